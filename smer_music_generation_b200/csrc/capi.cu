@@ -1,0 +1,35 @@
+// Library-level plumbing of the C ABI: version, per-thread error text, device queries.
+#include "common.cuh"
+#include "../../include/smer_b200.h"
+#include <stdarg.h>
+
+static thread_local char g_err[1024] = "";
+
+void smer_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int smer_num_sms() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+extern "C" int smer_version(void) { return SMER_B200_VERSION; }
+extern "C" const char* smer_last_error(void) { return g_err; }
+
+extern "C" int smer_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return major == 10 ? 1 : 0;
+}

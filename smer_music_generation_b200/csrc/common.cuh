@@ -1,0 +1,141 @@
+// Shared device/host helpers for the SMER B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define SMER_DT_F32 0
+#define SMER_DT_BF16 1
+
+#define SMER_OK 0
+#define SMER_ERR_ARG (-1)
+#define SMER_ERR_CUDA (-2)
+#define SMER_ERR_UNSUPPORTED (-3)
+
+typedef __nv_bfloat16 bf16;
+
+void smer_set_error(const char* fmt, ...);
+
+#define SMER_CHECK_ARG(cond, ...)                 \
+  do {                                            \
+    if (!(cond)) {                                \
+      smer_set_error(__VA_ARGS__);                \
+      return SMER_ERR_ARG;                        \
+    }                                             \
+  } while (0)
+
+#define SMER_CHECK_LAUNCH(name)                                              \
+  do {                                                                       \
+    cudaError_t e__ = cudaPeekAtLastError();                                 \
+    if (e__ != cudaSuccess) {                                                \
+      cudaGetLastError();                                                    \
+      smer_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return SMER_ERR_CUDA;                                                  \
+    }                                                                        \
+  } while (0)
+
+#define SMER_CUDA(call)                                                          \
+  do {                                                                           \
+    cudaError_t e__ = (call);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      smer_set_error("%s failed: %s", #call, cudaGetErrorString(e__));           \
+      return SMER_ERR_CUDA;                                                      \
+    }                                                                            \
+  } while (0)
+
+int smer_num_sms();
+
+// ---------------------------------------------------------------------------------------
+// element conversion
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-wide vector access (float4 for fp32, 8-byte for bf16)
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&a);
+}
+
+// ---------------------------------------------------------------------------------------
+// warp reductions
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG: stateless, so backward regenerates the forward's dropout mask
+// from (seed, site offset, element index) instead of storing it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32);
+  uint32_t c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// keep-mask for 4 consecutive elements starting at element index `idx4*4` of dropout site
+// `site`: returns per-element multiplier (0 or 1/(1-p)).  thr = p * 2^32.
+__device__ __forceinline__ void dropout4(uint64_t seed, uint64_t site, uint64_t idx4, uint32_t thr,
+                                         float inv_keep, float (&m)[4]) {
+  uint4 r = philox4x32(seed, idx4, site);
+  m[0] = r.x >= thr ? inv_keep : 0.f;
+  m[1] = r.y >= thr ? inv_keep : 0.f;
+  m[2] = r.z >= thr ? inv_keep : 0.f;
+  m[3] = r.w >= thr ? inv_keep : 0.f;
+}
+
+static inline uint32_t dropout_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}

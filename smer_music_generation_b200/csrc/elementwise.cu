@@ -1,0 +1,298 @@
+// Bandwidth-bound element-wise kernels: embedding*sqrt(d)+positional (+dropout) forward and
+// its scatter-add backward, dtype casts, bias-gradient column sums, mask inspection, Adam.
+// Reference arithmetic: model.py:91-92,110-125 (embed/PE), train.py:264,786 (Adam).
+#include "common.cuh"
+#include "../../include/smer_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// K1: out[b*L+l, :] = dropout(emb[ids[b,l], :] * scale + pe[l, :])
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
+                                    const float* __restrict__ pe, T* __restrict__ out, long long n4,
+                                    int L, int d4, int V, int pos0, float scale, uint32_t thr, float inv_keep,
+                                    uint64_t seed, uint64_t site) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / d4;
+    int c4 = (int)(i - row * d4);
+    int l = (int)(row % L) + pos0;
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    float e[4], p[4], o[4];
+    load4(emb + id * (long long)d4 * 4 + c4 * 4, e);
+    load4(pe + (long long)l * d4 * 4 + c4 * 4, p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = e[k] * scale + p[k];
+    if (thr) {
+      float m[4];
+      dropout4(seed, site, (uint64_t)i, thr, inv_keep, m);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] *= m[k];
+    }
+    store4(out + i * 4, o);
+  }
+}
+
+// demb[ids[row], :] += dout[row, :] * scale * dropmask   (fp32 vector reductions in L2)
+template <typename T>
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout,
+                                 float* __restrict__ demb, long long n4, int d4, int V, float scale,
+                                 uint32_t thr, float inv_keep, uint64_t seed, uint64_t site) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / d4;
+    int c4 = (int)(i - row * d4);
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    float g[4];
+    load4(dout + i * 4, g);
+    if (thr) {
+      float m[4];
+      dropout4(seed, site, (uint64_t)i, thr, inv_keep, m);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] *= m[k];
+    }
+    float* dst = demb + id * (long long)d4 * 4 + c4 * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g[0] * scale),
+                 "f"(g[1] * scale), "f"(g[2] * scale), "f"(g[3] * scale)
+                 : "memory");
+  }
+}
+
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  long long cap = (long long)smer_num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int smer_embed_pe_fwd(const int64_t* ids, const float* emb, const float* pe, void* out,
+                                 int out_dtype, int B, int L, int d, int V, int pos0, float scale,
+                                 float dropout_p, uint64_t seed, uint64_t site, void* stream) {
+  SMER_CHECK_ARG(d % 4 == 0 && B > 0 && L > 0, "smer_embed_pe_fwd: d must be a multiple of 4");
+  long long n4 = (long long)B * L * (d / 4);
+  uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+  float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(n4, 256);
+  if (out_dtype == SMER_DT_F32)
+    embed_pe_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, emb, pe, (float*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site);
+  else
+    embed_pe_fwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, emb, pe, (bf16*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site);
+  SMER_CHECK_LAUNCH("smer_embed_pe_fwd");
+  return SMER_OK;
+}
+
+extern "C" int smer_embed_bwd(const int64_t* ids, const void* dout, int dtype, float* demb, int B, int L,
+                              int d, int V, float scale, float dropout_p, uint64_t seed, uint64_t site,
+                              void* stream) {
+  SMER_CHECK_ARG(d % 4 == 0, "smer_embed_bwd: d must be a multiple of 4");
+  long long n4 = (long long)B * L * (d / 4);
+  uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+  float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(n4, 256);
+  if (dtype == SMER_DT_F32)
+    embed_bwd_kernel<float><<<grid, 256, 0, st>>>(ids, (const float*)dout, demb, n4, d / 4, V, scale, thr, inv_keep, seed, site);
+  else
+    embed_bwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, (const bf16*)dout, demb, n4, d / 4, V, scale, thr, inv_keep, seed, site);
+  SMER_CHECK_LAUNCH("smer_embed_bwd");
+  return SMER_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// casts: 2-D copy with independent row strides and dtype; columns beyond `cols` up to
+// `dst_cols` are zero-filled (pads V=309 to an aligned row pitch for the GEMMs).
+// ---------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void cast2d_kernel(const TS* __restrict__ src, long long src_ld, TD* __restrict__ dst,
+                              long long dst_ld, long long rows, int cols, int dst_cols) {
+  long long n = rows * dst_cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / dst_cols;
+    int c = (int)(i - r * dst_cols);
+    float v = c < cols ? to_f32(src[r * src_ld + c]) : 0.f;
+    dst[r * dst_ld + c] = from_f32<TD>(v);
+  }
+}
+
+extern "C" int smer_cast2d(const void* src, int src_dtype, long long src_ld, void* dst, int dst_dtype,
+                           long long dst_ld, long long rows, int cols, int dst_cols, void* stream) {
+  SMER_CHECK_ARG(dst_cols >= cols && rows >= 0, "smer_cast2d: bad shape");
+  if (rows == 0) return SMER_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(rows * dst_cols, 256);
+  if (src_dtype == SMER_DT_F32 && dst_dtype == SMER_DT_BF16)
+    cast2d_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, src_ld, (bf16*)dst, dst_ld, rows, cols, dst_cols);
+  else if (src_dtype == SMER_DT_BF16 && dst_dtype == SMER_DT_F32)
+    cast2d_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, src_ld, (float*)dst, dst_ld, rows, cols, dst_cols);
+  else if (src_dtype == SMER_DT_F32 && dst_dtype == SMER_DT_F32)
+    cast2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, rows, cols, dst_cols);
+  else
+    cast2d_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, rows, cols, dst_cols);
+  SMER_CHECK_LAUNCH("smer_cast2d");
+  return SMER_OK;
+}
+
+// flat fp32 -> bf16 shadow of the parameter arena (one launch per step)
+__global__ void cast_flat_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[4];
+    load4(src + i * 4, v);
+    store4(dst + i * 4, v);
+  }
+}
+
+extern "C" int smer_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  SMER_CHECK_ARG(n % 4 == 0, "smer_cast_f32_to_bf16: n must be a multiple of 4");
+  if (n == 0) return SMER_OK;
+  cast_flat_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n / 4);
+  SMER_CHECK_LAUNCH("smer_cast_f32_to_bf16");
+  return SMER_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// bias gradient: out[c] (+)= sum_r x[r, c].   Block = 32x8 threads; each block owns a 32-column
+// strip and a slab of rows, reduces in shared memory and issues one atomic per column.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, long long rows,
+                              int cols, long long rows_per_block) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f32(x[r * ld + c]);
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sm[k][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+extern "C" int smer_colsum(const void* x, int dtype, long long ld, float* out, long long rows, int cols,
+                           void* stream) {
+  if (rows == 0 || cols == 0) return SMER_OK;
+  int gx = (cols + 31) / 32;
+  long long target = (long long)smer_num_sms() * 8 / gx;
+  if (target < 1) target = 1;
+  long long rpb = (rows + target - 1) / target;
+  if (rpb < 64) rpb = 64;
+  int gy = (int)((rows + rpb - 1) / rpb);
+  dim3 grid(gx, gy), block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMER_DT_F32)
+    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, out, rows, cols, rpb);
+  else
+    colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, ld, out, rows, cols, rpb);
+  SMER_CHECK_LAUNCH("smer_colsum");
+  return SMER_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Mask inspection.  kv_len[b] = 1 + index of the last un-padded key (A0: pads are a suffix,
+// but the attention kernels still honour the per-key mask; kv_len only bounds the key loop).
+// ---------------------------------------------------------------------------------------
+__global__ void kv_len_kernel(const uint8_t* __restrict__ pad, int* __restrict__ kv_len, int L) {
+  int b = blockIdx.x;
+  int best = 0;
+  for (int j = threadIdx.x; j < L; j += blockDim.x)
+    if (!pad[(long long)b * L + j]) best = j + 1;
+  __shared__ int sm[32];
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = max(m, sm[w]);
+    kv_len[b] = m;
+  }
+}
+
+extern "C" int smer_kv_len_from_pad(const uint8_t* pad, int* kv_len, int B, int L, void* stream) {
+  kv_len_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pad, kv_len, L);
+  SMER_CHECK_LAUNCH("smer_kv_len_from_pad");
+  return SMER_OK;
+}
+
+// Classifies a (T,T) additive float mask: flag = 0 all-zero, 1 exactly the nopeek mask
+// (0 on/below the diagonal, -inf above; generation.py:193-206), 2 anything else.
+__global__ void classify_mask_kernel(const float* __restrict__ m, long long ld, int T, int* __restrict__ flags) {
+  // flags[0]: any non-zero on/below diagonal or any value other than 0/-inf above; flags[1]: any non -inf above
+  // flags[2]: any non-zero above
+  int bad = 0, not_inf_above = 0, nonzero_above = 0;
+  long long n = (long long)T * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(i / T), c = (int)(i - (long long)r * T);
+    float v = m[r * ld + c];
+    if (c <= r) {
+      if (v != 0.f) bad = 1;
+    } else {
+      if (v != 0.f) nonzero_above = 1;
+      if (!(isinf(v) && v < 0.f)) not_inf_above = 1;
+    }
+  }
+  if (bad) atomicOr(flags + 0, 1);
+  if (not_inf_above) atomicOr(flags + 1, 1);
+  if (nonzero_above) atomicOr(flags + 2, 1);
+}
+
+extern "C" int smer_classify_mask(const float* mask, long long ld, int T, int* flags3, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SMER_CUDA(cudaMemsetAsync(flags3, 0, 3 * sizeof(int), st));
+  classify_mask_kernel<<<grid_for((long long)T * T, 256), 256, 0, st>>>(mask, ld, T, flags3);
+  SMER_CHECK_LAUNCH("smer_classify_mask");
+  return SMER_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Adam (train.py:264: torch.optim.Adam defaults -- no weight decay, no amsgrad), one launch
+// over the flat parameter arena; optionally refreshes the bf16 shadow in the same pass.
+// ---------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, bf16* __restrict__ shadow, long long n4, float lr, float b1,
+                            float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float pp[4], gg[4], mm[4], vv[4];
+    load4(p + i * 4, pp);
+    load4(g + i * 4, gg);
+    load4(m + i * 4, mm);
+    load4(v + i * 4, vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = gg[k] * gscale;
+      mm[k] = b1 * mm[k] + (1.f - b1) * gk;
+      vv[k] = b2 * vv[k] + (1.f - b2) * gk * gk;
+      float denom = sqrtf(vv[k]) / bc2_sqrt + eps;
+      pp[k] -= (lr / bc1) * (mm[k] / denom);
+    }
+    store4(p + i * 4, pp);
+    store4(m + i * 4, mm);
+    store4(v + i * 4, vv);
+    if (shadow) store4(shadow + i * 4, pp);
+  }
+}
+
+extern "C" int smer_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
+                              int step, float lr, float beta1, float beta2, float eps, float grad_scale,
+                              void* stream) {
+  SMER_CHECK_ARG(n % 4 == 0 && step >= 1, "smer_adam_step: n must be a multiple of 4 and step >= 1");
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)bf16_shadow, n / 4, lr, beta1,
+                                                                   beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  SMER_CHECK_LAUNCH("smer_adam_step");
+  return SMER_OK;
+}

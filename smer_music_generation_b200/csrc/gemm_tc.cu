@@ -1,0 +1,323 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory
+// ring -> tcgen05.mma (single issuing thread, fp32 accumulators in TMEM) -> tcgen05.ld epilogue.
+//     C[M,N] = epilogue( A . B^T ),   A: M x K,  B: N x K   (either may be stored transposed)
+// Serves every nn.Linear product of the reference's stack (transformer.py:362-364 linear1/2,
+// MultiheadAttention in/out projections, model.py:82 fc) and both backward products
+// (dX = dY.W uses B MN-major; dW = dY^T.X uses A and B MN-major with split-K fp32 atomics).
+//
+// CTA = 128x128 output tile, K step 64, 3-stage ring (96 KB) so two CTAs share an SM and one
+// CTA's epilogue overlaps the other's main loop; 128 TMEM columns per CTA.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue (TMEM lane
+// quarter = warp_idx % 4).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/smer_b200.h"
+#include <mutex>
+#include <unordered_map>
+#include <string>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB per operand per stage
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct EpiParams {
+  void* C;
+  long long ldc;
+  const float* bias;
+  const void* resid;
+  long long ldr;
+  int M, N;
+  int flags;
+  uint32_t thr;
+  float inv_keep;
+  uint64_t seed, site;
+  int kb_per_split, num_kb;
+};
+
+template <bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * TILE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGES * TILE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar + s, 1);
+      ptx::mbar_init(empty_bar + s, 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<128>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        ptx::mbar_wait(empty_bar + s, ((i / STAGES) & 1) ^ 1);
+        ptx::mbar_expect_tx(full_bar + s, 2 * TILE_BYTES);
+        const int k = (kb0 + i) * BK;
+        uint8_t* a = sA + s * TILE_BYTES;
+        uint8_t* b = sB + s * TILE_BYTES;
+        if (!A_MN) {
+          ptx::tma_load_2d(a, &tmap_a, full_bar + s, k, m0);
+        } else {
+          ptx::tma_load_2d(a, &tmap_a, full_bar + s, m0, k);
+          ptx::tma_load_2d(a + TILE_BYTES / 2, &tmap_a, full_bar + s, m0 + 64, k);
+        }
+        if (!B_MN) {
+          ptx::tma_load_2d(b, &tmap_b, full_bar + s, k, n0);
+        } else {
+          ptx::tma_load_2d(b, &tmap_b, full_bar + s, n0, k);
+          ptx::tma_load_2d(b + TILE_BYTES / 2, &tmap_b, full_bar + s, n0 + 64, k);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        ptx::mbar_wait(full_bar + s, (i / STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t a = ptx::smem_u32(sA + s * TILE_BYTES);
+        const uint32_t b = ptx::smem_u32(sB + s * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: 16 elements = 32 B inside the 128 B swizzle row; rows 8 apart are 1024 B apart.
+          // MN-major: 16 k-rows = 2048 B; 64-element MN chunks are 8192 B apart, 8-row groups 1024 B.
+          const uint64_t ad = A_MN ? ptx::make_smem_desc(a + k * 2048, 8192, 1024) : ptx::make_smem_desc(a + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? ptx::make_smem_desc(b + k * 2048, 8192, 1024) : ptx::make_smem_desc(b + k * 32, 16, 1024);
+          ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(empty_bar + s);        // frees the smem stage once these MMAs have read it
+      }
+      ptx::umma_commit(tmem_full_bar);          // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+    TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
+    const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 32; g += 4) {
+        const int col = n0 + c0 + g;
+        if (col >= p.N) break;
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(r[g + u]);
+        if (p.flags & SMER_EPI_ATOMIC) {
+          if (p.bias && blockIdx.z == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] += p.bias[col + u];
+          }
+          float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3])
+                       : "memory");
+          continue;
+        }
+        if (p.bias) {
+          float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+          v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+        }
+        if (p.flags & SMER_EPI_RELU) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = fmaxf(v[u], 0.f);
+        }
+        if (p.flags & SMER_EPI_GATE) {
+          float gte[4];
+          load4(rrow + col, gte);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
+        } else {
+          if (p.thr) {
+            float m[4];
+            dropout4(p.seed, p.site, (uint64_t)(((long long)row * p.ldc + col) >> 2), p.thr, p.inv_keep, m);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] *= m[u];
+          }
+          if (rrow) {
+            float rs[4];
+            load4(rrow + col, rs);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] += rs[u];
+          }
+          if (p.flags & SMER_EPI_ACCUM) {
+            float old[4];
+            load4(crow + col, old);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] += old[u];
+          }
+        }
+        store4(crow + col, v);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<128>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched at run time, no -lcuda)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long inner, outer, pitch;
+  int box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch == o.pitch && box_inner == o.box_inner &&
+           box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    auto mix = [&h](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.inner); mix(k.outer); mix(k.pitch); mix(k.box_inner); mix(k.box_outer);
+    return h;
+  }
+};
+
+}  // namespace
+
+// bf16 2-D tensor map: `inner` contiguous elements per row, `outer` rows, row pitch in elements.
+int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
+                        int box_inner, int box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, inner, outer, pitch, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return SMER_OK; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { smer_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return SMER_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch * 2) % 16) {
+    smer_set_error("TMA operand needs a 16-byte aligned base and pitch (ptr=%p pitch=%lld elements)", ptr, pitch);
+    return SMER_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    smer_set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld pitch=%lld box=%dx%d", (int)r, inner, outer,
+                   pitch, box_inner, box_outer);
+    return SMER_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return SMER_OK;
+}
+
+template <bool A_MN, bool B_MN, typename TC>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMER_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_tc_kernel<A_MN, B_MN, TC><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  return SMER_OK;
+}
+
+extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor,
+                                 void* C, long long ldc, int out_dtype, int M, int N, int K, const float* bias,
+                                 const void* resid, long long ldr, int flags, float dropout_p, uint64_t seed,
+                                 uint64_t site, int split_k, void* stream) {
+  SMER_CHECK_ARG(M > 0 && N > 0 && K > 0, "smer_gemm_bf16_tc: empty problem %dx%dx%d", M, N, K);
+  SMER_CHECK_ARG(N % 8 == 0 && ldc % 4 == 0, "smer_gemm_bf16_tc: need N%%8==0 and ldc%%4==0 (N=%d ldc=%lld)", N, ldc);
+  if (split_k < 1) split_k = 1;
+  SMER_CHECK_ARG(split_k == 1 || ((flags & SMER_EPI_ATOMIC) && out_dtype == SMER_DT_F32),
+                 "smer_gemm_bf16_tc: split_k needs SMER_EPI_ATOMIC and fp32 output");
+  SMER_CHECK_ARG(!(flags & SMER_EPI_ATOMIC) || out_dtype == SMER_DT_F32, "smer_gemm_bf16_tc: atomic epilogue needs fp32 output");
+  SMER_CHECK_ARG(!(flags & SMER_EPI_GATE) || resid, "smer_gemm_bf16_tc: gate epilogue needs the activation in `resid`");
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_kmajor) rc = smer_make_tmap_bf16(&ta, A, K, M, lda, BK, BM);
+  else rc = smer_make_tmap_bf16(&ta, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (b_kmajor) rc = smer_make_tmap_bf16(&tb, B, K, N, ldb, BK, BN);
+  else rc = smer_make_tmap_bf16(&tb, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  EpiParams p;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.resid = resid; p.ldr = ldr; p.M = M; p.N = N; p.flags = flags;
+  p.thr = (dropout_p > 0.f && !(flags & SMER_EPI_GATE)) ? dropout_threshold(dropout_p) : 0u;
+  p.inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  p.seed = seed; p.site = site;
+  p.num_kb = (K + BK - 1) / BK;
+  if (split_k > p.num_kb) split_k = p.num_kb;
+  p.kb_per_split = (p.num_kb + split_k - 1) / split_k;
+  split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;       // no empty splits
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool amn = !a_kmajor, bmn = !b_kmajor, f32 = out_dtype == SMER_DT_F32;
+#define GO(AM, BMN, T) rc = launch_gemm<AM, BMN, T>(ta, tb, p, grid, st)
+  if (!amn && !bmn) { if (f32) GO(false, false, float); else GO(false, false, bf16); }
+  else if (!amn && bmn) { if (f32) GO(false, true, float); else GO(false, true, bf16); }
+  else if (amn && !bmn) { if (f32) GO(true, false, float); else GO(true, false, bf16); }
+  else { if (f32) GO(true, true, float); else GO(true, true, bf16); }
+#undef GO
+  if (rc) return rc;
+  SMER_CHECK_LAUNCH("smer_gemm_bf16_tc");
+  return SMER_OK;
+}

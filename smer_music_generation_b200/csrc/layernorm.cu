@@ -1,0 +1,259 @@
+// Fused residual-add (+dropout on the branch) + LayerNorm, forward and backward.
+// Reference: transformer.py:391-392,394-395 (encoder), 461-462,465-466,468-469 (decoder):
+//     x = norm(x + dropout(branch)),  nn.LayerNorm(d), eps 1e-5, affine.
+// HBM-bound: one warp per row, 16-byte (fp32) / 8-byte (bf16) vector accesses, the row is
+// held in registers between the statistics pass and the normalisation pass.
+#include "common.cuh"
+#include "../../include/smer_b200.h"
+
+constexpr int LN_MAX_ITERS = 8;   // d <= 8 * 128 = 1024
+
+template <typename T, int ITERS>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const float* __restrict__ gamma,
+              const float* __restrict__ beta, T* __restrict__ z_out, T* __restrict__ y, float* __restrict__ mean,
+              float* __restrict__ rstd, long long rows, int d, float eps, uint32_t thr, float inv_keep,
+              uint64_t seed, uint64_t site) {
+  int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  int d4 = d >> 2;
+  for (long long row = warp; row < rows; row += nwarps) {
+    float v[ITERS][4];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      int c4 = lane + it * 32;
+      if (c4 < d4) {
+        long long off = row * d + c4 * 4;
+        load4(branch + off, v[it]);
+        if (thr) {
+          float m[4];
+          dropout4(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[it][k] *= m[k];
+        }
+        if (resid) {
+          float r[4];
+          load4(resid + off, r);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[it][k] += r[k];
+        }
+        if (z_out) {
+          store4(z_out + off, v[it]);
+          // statistics are taken on the values as stored so that backward (which re-reads z)
+          // sees exactly the same normalisation input
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[it][k] = to_f32(from_f32<T>(v[it][k]));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += v[it][k];
+      }
+    }
+    float mu = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      int c4 = lane + it * 32;
+      if (c4 < d4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t = v[it][k] - mu;
+          q += t * t;
+        }
+      }
+    }
+    float rs = rsqrtf(warp_sum(q) / d + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      int c4 = lane + it * 32;
+      if (c4 < d4) {
+        float g[4], b[4], o[4];
+        load4(gamma + c4 * 4, g);
+        load4(beta + c4 * 4, b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (v[it][k] - mu) * rs * g[k] + b[k];
+        store4(y + row * d + c4 * 4, o);
+      }
+    }
+  }
+}
+
+// dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy.
+// d_branch = dz * dropmask (written only when dropout is on; otherwise the caller aliases dz).
+template <typename T, int ITERS>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz,
+              T* __restrict__ dbranch, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int d,
+              uint32_t thr, float inv_keep, uint64_t seed, uint64_t site) {
+  extern __shared__ float sm[];   // [2][warps][d]
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  long long warp = (long long)blockIdx.x * nw + wib;
+  long long nwarps = (long long)gridDim.x * nw;
+  int d4 = d >> 2;
+  float ag[ITERS][4], ab[ITERS][4], g[ITERS][4];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    int c4 = lane + it * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ag[it][k] = ab[it][k] = 0.f;
+    if (c4 < d4) load4(gamma + c4 * 4, g[it]);
+  }
+  for (long long row = warp; row < rows; row += nwarps) {
+    float mu = mean[row], rs = rstd[row];
+    float xh[ITERS][4], gy[ITERS][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      int c4 = lane + it * 32;
+      if (c4 < d4) {
+        float a[4], zz[4];
+        load4(dy + row * d + c4 * 4, a);
+        load4(z + row * d + c4 * 4, zz);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xh[it][k] = (zz[k] - mu) * rs;
+          ab[it][k] += a[k];
+          ag[it][k] += a[k] * xh[it][k];
+          gy[it][k] = a[k] * g[it][k];
+          s1 += gy[it][k];
+          s2 += gy[it][k] * xh[it][k];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      int c4 = lane + it * 32;
+      if (c4 < d4) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = rs * (gy[it][k] - s1 - xh[it][k] * s2);
+        store4(dz + row * d + c4 * 4, o);
+        if (dbranch) {
+          if (thr) {
+            float m[4];
+            dropout4(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] *= m[k];
+          }
+          store4(dbranch + row * d + c4 * 4, o);
+        }
+      }
+    }
+  }
+  // block reduction of the column sums, then one atomic per column per block
+  float* sg = sm;
+  float* sb = sm + nw * d;
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    int c4 = lane + it * 32;
+    if (c4 < d4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sg[wib * d + c4 * 4 + k] = ag[it][k];
+        sb[wib * d + c4 * 4 + k] = ab[it][k];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float tg = 0.f, tb = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      tg += sg[w * d + c];
+      tb += sb[w * d + c];
+    }
+    atomicAdd(dgamma + c, tg);
+    atomicAdd(dbeta + c, tb);
+  }
+}
+
+template <typename T>
+static int ln_fwd_launch(const void* branch, const void* resid, const float* gamma, const float* beta, void* z,
+                         void* y, float* mean, float* rstd, long long rows, int d, float eps, uint32_t thr,
+                         float inv_keep, uint64_t seed, uint64_t site, cudaStream_t st) {
+  int iters = (d / 4 + 31) / 32;
+  long long blocks = (rows + 7) / 8;
+  long long cap = (long long)smer_num_sms() * 8;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  if (grid < 1) grid = 1;
+#define LN_CASE(I)                                                                                          \
+  case I:                                                                                                   \
+    ln_fwd_kernel<T, I><<<grid, 256, 0, st>>>((const T*)branch, (const T*)resid, gamma, beta, (T*)z, (T*)y, mean, \
+                                              rstd, rows, d, eps, thr, inv_keep, seed, site);              \
+    break;
+  switch (iters) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+    default:
+      smer_set_error("smer_layernorm_fwd: d=%d unsupported (max 1024)", d);
+      return SMER_ERR_UNSUPPORTED;
+  }
+#undef LN_CASE
+  return SMER_OK;
+}
+
+extern "C" int smer_layernorm_fwd(const void* branch, const void* resid, const float* gamma, const float* beta,
+                                  void* z_out, void* y, float* mean, float* rstd, int dtype, long long rows,
+                                  int d, float eps, float dropout_p, uint64_t seed, uint64_t site, void* stream) {
+  SMER_CHECK_ARG(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_ITERS, "smer_layernorm_fwd: need d%%4==0 and d<=1024 (got %d)", d);
+  if (rows == 0) return SMER_OK;
+  uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+  float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dtype == SMER_DT_F32
+               ? ln_fwd_launch<float>(branch, resid, gamma, beta, z_out, y, mean, rstd, rows, d, eps, thr, inv_keep, seed, site, st)
+               : ln_fwd_launch<bf16>(branch, resid, gamma, beta, z_out, y, mean, rstd, rows, d, eps, thr, inv_keep, seed, site, st);
+  if (rc) return rc;
+  SMER_CHECK_LAUNCH("smer_layernorm_fwd");
+  return SMER_OK;
+}
+
+template <typename T>
+static int ln_bwd_launch(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
+                         void* dz, void* dbranch, float* dgamma, float* dbeta, long long rows, int d, uint32_t thr,
+                         float inv_keep, uint64_t seed, uint64_t site, cudaStream_t st) {
+  int iters = (d / 4 + 31) / 32;
+  long long blocks = (rows + 7) / 8;
+  long long cap = (long long)smer_num_sms() * 2;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  if (grid < 1) grid = 1;
+  size_t smem = 2 * 8 * (size_t)d * sizeof(float);
+#define LN_CASE(I)                                                                                              \
+  case I:                                                                                                       \
+    if (smem > 48 * 1024)                                                                                       \
+      cudaFuncSetAttribute(ln_bwd_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    ln_bwd_kernel<T, I><<<grid, 256, smem, st>>>((const T*)dy, (const T*)z, mean, rstd, gamma, (T*)dz, (T*)dbranch, \
+                                                 dgamma, dbeta, rows, d, thr, inv_keep, seed, site);            \
+    break;
+  switch (iters) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+    default:
+      smer_set_error("smer_layernorm_bwd: d=%d unsupported (max 1024)", d);
+      return SMER_ERR_UNSUPPORTED;
+  }
+#undef LN_CASE
+  return SMER_OK;
+}
+
+extern "C" int smer_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd,
+                                  const float* gamma, void* dz, void* dbranch, float* dgamma, float* dbeta,
+                                  int dtype, long long rows, int d, float dropout_p, uint64_t seed, uint64_t site,
+                                  void* stream) {
+  SMER_CHECK_ARG(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_ITERS, "smer_layernorm_bwd: need d%%4==0 and d<=1024 (got %d)", d);
+  if (rows == 0) return SMER_OK;
+  uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+  float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dtype == SMER_DT_F32
+               ? ln_bwd_launch<float>(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, rows, d, thr, inv_keep, seed, site, st)
+               : ln_bwd_launch<bf16>(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, rows, d, thr, inv_keep, seed, site, st);
+  if (rc) return rc;
+  SMER_CHECK_LAUNCH("smer_layernorm_bwd");
+  return SMER_OK;
+}

@@ -1,0 +1,200 @@
+"""Tensor-level wrappers over the C ABI (one function per kernel family).  All tensors are CUDA
+tensors owned by PyTorch's caching allocator; kernels are enqueued on the current stream."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional
+
+import torch
+
+from . import _capi as K
+
+_TC_GEMM = os.environ.get("SMER_GEMM", "tc")     # "simt" forces the CUDA-core GEMM (debug aid)
+_TC_ATTN = os.environ.get("SMER_ATTN", "tc")
+_NUM_SMS = None
+
+
+def num_sms() -> int:
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _NUM_SMS
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def embed_pe(ids, emb, pe, out, scale, pos0=0, dropout_p=0.0, seed=0, site=0):
+    B, L = ids.shape
+    V, d = emb.shape
+    K.check(K.lib().smer_embed_pe_fwd(_p(ids), _p(emb), _p(pe), _p(out), K.dt(out), B, L, d, V, pos0, scale,
+                                      dropout_p, seed, site, K.stream()), "embed_pe_fwd")
+
+
+def embed_bwd(ids, dout, demb, scale, dropout_p=0.0, seed=0, site=0):
+    B, L = ids.shape
+    V, d = demb.shape
+    K.check(K.lib().smer_embed_bwd(_p(ids), _p(dout), K.dt(dout), _p(demb), B, L, d, V, scale, dropout_p, seed,
+                                   site, K.stream()), "embed_bwd")
+
+
+def layernorm_fwd(branch, resid, gamma, beta, z_out, y, mean, rstd, eps=1e-5, dropout_p=0.0, seed=0, site=0):
+    rows, d = branch.shape
+    K.check(K.lib().smer_layernorm_fwd(_p(branch), _p(resid), _p(gamma), _p(beta), _p(z_out), _p(y), _p(mean),
+                                       _p(rstd), K.dt(branch), rows, d, eps, dropout_p, seed, site, K.stream()),
+            "layernorm_fwd")
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dropout_p=0.0, seed=0, site=0):
+    rows, d = dy.shape
+    K.check(K.lib().smer_layernorm_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dbranch),
+                                       _p(dgamma), _p(dbeta), K.dt(dy), rows, d, dropout_p, seed, site, K.stream()),
+            "layernorm_bwd")
+
+
+def _tc_ok(a_dtype, N, ldc, *pitches):
+    return (_TC_GEMM == "tc" and a_dtype == torch.bfloat16 and N % 8 == 0 and ldc % 4 == 0
+            and all(p % 8 == 0 for p in pitches))
+
+
+def gemm_nt(A, W, out, bias=None, resid=None, flags=0, dropout_p=0.0, seed=0, site=0):
+    """out[M,N] = epi(A[M,K] @ W[N,K]^T) -- nn.Linear forward.  A/out may be strided row views."""
+    M, Kd = A.shape
+    N = W.shape[0]
+    lda, ldw, ldc = A.stride(0), W.stride(0), out.stride(0)
+    ldr = resid.stride(0) if resid is not None else 0
+    if _tc_ok(A.dtype, N, ldc, lda, ldw):
+        K.check(K.lib().smer_gemm_bf16_tc(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(out), M, N, Kd, _p(bias),
+                                          _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()), "gemm_tc(nt)")
+    else:
+        K.check(K.lib().smer_gemm_simt(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(A), K.dt(out), M, N, Kd,
+                                       _p(bias), _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()),
+                "gemm_simt(nt)")
+
+
+def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0):
+    """out[M,Kin] = epi(dY[M,N] @ W[N,Kin]) -- input gradient of nn.Linear."""
+    M, N = dY.shape
+    Kin = W.shape[1]
+    ldy, ldw, ldc = dY.stride(0), W.stride(0), out.stride(0)
+    ldr = resid.stride(0) if resid is not None else 0
+    if _tc_ok(dY.dtype, Kin, ldc, ldy, ldw):
+        K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 1, _p(W), ldw, 0, _p(out), ldc, K.dt(out), M, Kin, N, 0,
+                                          _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_tc(dx)")
+    else:
+        K.check(K.lib().smer_gemm_simt(_p(dY), ldy, 1, _p(W), 1, ldw, _p(out), ldc, K.dt(dY), K.dt(out), M, Kin, N,
+                                       0, _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_simt(dx)")
+
+
+def gemm_dw(dY, X, out):
+    """out[N,Kin] += dY[M,N]^T @ X[M,Kin] (fp32, `out` pre-zeroed) -- weight gradient of nn.Linear."""
+    M, N = dY.shape
+    Kin = X.shape[1]
+    ldy, ldx, ldc = dY.stride(0), X.stride(0), out.stride(0)
+    if _tc_ok(dY.dtype, Kin, ldc, ldy, ldx):
+        tiles = ((N + 127) // 128) * ((Kin + 127) // 128)
+        split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
+        K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 0, _p(X), ldx, 0, _p(out), ldc, K.F32, N, Kin, M, 0, 0, 0,
+                                          K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_tc(dw)")
+    else:
+        tiles = ((N + 63) // 64) * ((Kin + 63) // 64)
+        split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
+        K.check(K.lib().smer_gemm_simt(_p(dY), 1, ldy, _p(X), 1, ldx, _p(out), ldc, K.dt(dY), K.F32, N, Kin, M, 0, 0,
+                                       0, K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_simt(dw)")
+
+
+def colsum(x, out):
+    rows, cols = x.shape
+    K.check(K.lib().smer_colsum(_p(x), K.dt(x), x.stride(0), _p(out), rows, cols, K.stream()), "colsum")
+
+
+def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0, key_pad=None, kv_len=None,
+              add_mask=None, dropout_p=0.0, seed=0, site=0, dout=None, dq=None, dk=None, dv=None, dsum=None):
+    a = K.AttnArgs()
+    a.q, a.k, a.v, a.o = _p(q), _p(k), _p(v), _p(o)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    a.dout, a.dq, a.dk, a.dv = _p(dout), _p(dq), _p(dk), _p(dv)
+    a.lddo = dout.stride(0) if dout is not None else 0
+    a.lddq = dq.stride(0) if dq is not None else 0
+    a.lddk = dk.stride(0) if dk is not None else 0
+    a.lddv = dv.stride(0) if dv is not None else 0
+    a.lse, a.dsum = _p(lse), _p(dsum)
+    a.key_pad, a.kv_len = _p(key_pad), _p(kv_len)
+    a.add_mask = _p(add_mask)
+    a.ld_mask = add_mask.stride(0) if add_mask is not None else 0
+    a.B, a.H, a.Lq, a.Lk, a.dh = B, H, Lq, Lk, dh
+    a.dtype = K.dt(q)
+    a.causal, a.q_pos0 = int(causal), q_pos0
+    a.scale = 1.0 / math.sqrt(dh)
+    a.dropout_p, a.seed, a.site = dropout_p, seed, site
+    return a
+
+
+def _attn_tc_ok(a) -> bool:
+    return _TC_ATTN == "tc" and a.dtype == K.BF16 and a.dh == 64 and not a.add_mask and a.q_pos0 == 0
+
+
+def attn_fwd(a):
+    if _attn_tc_ok(a) and ATTN_TC_FWD:
+        K.check(K.lib().smer_attn_fwd_tc(C.byref(a), K.stream()), "attn_fwd_tc")
+    else:
+        K.check(K.lib().smer_attn_fwd_simt(C.byref(a), K.stream()), "attn_fwd_simt")
+
+
+def attn_bwd(a):
+    if _attn_tc_ok(a) and ATTN_TC_BWD:
+        K.check(K.lib().smer_attn_bwd_tc(C.byref(a), K.stream()), "attn_bwd_tc")
+    else:
+        K.check(K.lib().smer_attn_bwd_simt(C.byref(a), K.stream()), "attn_bwd_simt")
+
+
+def attn_weights(a, w):
+    K.check(K.lib().smer_attn_weights(C.byref(a), _p(w), w.stride(-2), K.stream()), "attn_weights")
+
+
+# Which tcgen05 attention kernels this build provides (attn_tc.cu); the dispatcher above is a
+# capability table of the one library, not a backend switch.
+ATTN_TC_FWD = False
+ATTN_TC_BWD = False
+
+
+def xent_fwd(logits, targets, W, Cw, category, ncat, lse, sums, V):
+    rows = logits.shape[0]
+    K.check(K.lib().smer_xent_fwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(Cw), _p(category), ncat,
+                                  _p(lse), _p(sums), rows, V, K.stream()), "xent_fwd")
+
+
+def xent_bwd(logits, targets, W, lse, sums, dlogits, V, grad_scale=1.0):
+    rows = logits.shape[0]
+    K.check(K.lib().smer_xent_bwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(lse), _p(sums), _p(dlogits),
+                                  K.dt(dlogits), dlogits.stride(0), rows, V, dlogits.shape[1], grad_scale,
+                                  K.stream()), "xent_bwd")
+
+
+def adam_step(p, g, m, v, shadow, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+    K.check(K.lib().smer_adam_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), step, lr, b1, b2, eps,
+                                   grad_scale, K.stream()), "adam_step")
+
+
+def cast2d(src, dst, cols=None):
+    rows = src.shape[0]
+    cols = src.shape[1] if cols is None else cols
+    K.check(K.lib().smer_cast2d(_p(src), K.dt(src), src.stride(0), _p(dst), K.dt(dst), dst.stride(0), rows, cols,
+                                dst.shape[1], K.stream()), "cast2d")
+
+
+def cast_f32_to_bf16(src, dst):
+    K.check(K.lib().smer_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), K.stream()), "cast_f32_to_bf16")
+
+
+def kv_len_from_pad(pad_u8, out):
+    B, L = pad_u8.shape
+    K.check(K.lib().smer_kv_len_from_pad(_p(pad_u8), _p(out), B, L, K.stream()), "kv_len_from_pad")
+
+
+def classify_mask(mask2d, flags3):
+    T = mask2d.shape[0]
+    K.check(K.lib().smer_classify_mask(_p(mask2d), mask2d.stride(0), T, _p(flags3), K.stream()), "classify_mask")
