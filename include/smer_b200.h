@@ -118,7 +118,8 @@ int smer_xent_fwd(const float* logits, long long ld, const int64_t* targets, con
                   const int* category, int ncat, float* lse, double* sums, long long rows, int V, void* stream);
 int smer_xent_bwd(const float* logits, long long ld, const int64_t* targets, const float* W, const float* lse,
                   const double* sums, void* dlogits, int out_dtype, long long ldo, long long rows, int V,
-                  int Vpad, float grad_scale, void* stream);
+                  int Vpad, float grad_scale, const float* grad_scale_dev /* device scalar or NULL */,
+                  void* stream);
 
 /* ---- K11: Adam.  train.py:264,786 ------------------------------------------------------------ */
 int smer_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
@@ -139,8 +140,9 @@ typedef struct smer_decode_attn_args {
 } smer_decode_attn_args;
 long long smer_decode_attn_workspace_bytes(int n_seq, int H, int dh, int splits);
 int smer_decode_attn(const smer_decode_attn_args* a, void* stream);
-int smer_decode_gather(const int64_t* tok_buf, const int* cur_len, int64_t* ids, int* pos, int n_seq,
-                       int max_len, void* stream);
+/* ids[s] = tok_buf[s, p], pos[s] = p with p = min(fed_len[s], cur_len[s]-1) (fed_len NULL: cur_len-1) */
+int smer_decode_gather(const int64_t* tok_buf, const int* cur_len, const int* fed_len, int64_t* ids, int* pos,
+                       int n_seq, int max_len, void* stream);
 int smer_embed_step(const int64_t* ids, const int* pos, const float* emb, const float* pe, void* out,
                     int out_dtype, int n_seq, int d, int V, float scale, void* stream);
 
@@ -165,6 +167,7 @@ typedef struct smer_sample_args {
   /* decoder input stream bookkeeping (generation.py:673-686) */
   int64_t* tok_buf;           /* [n_seq, max_len]                                             */
   int *cur_len, *span_start, *span_idx;
+  int* fed_len;               /* tokens whose K/V are cached (next position to feed), or NULL */
   const int* n_spans;
   int *done, *gen_count;
   const uint32_t* control_bitmap; /* bit i set: id i is in the caller's all_controls list      */

@@ -44,7 +44,7 @@ class SampleArgs(C.Structure):
                 ("top_p", _f), ("top_k", _i), ("seed", _u64), ("seq_base", _ll), ("step_base", _u64),
                 ("state", _vp), ("targets", _vp), ("nwd", _vp), ("max_spans", _i), ("raw_flags", _vp),
                 ("raw_only_lo", _vp), ("raw_only_hi", _vp), ("tok_buf", _vp), ("cur_len", _vp), ("span_start", _vp),
-                ("span_idx", _vp), ("n_spans", _vp), ("done", _vp), ("gen_count", _vp), ("control_bitmap", _vp),
+                ("span_idx", _vp), ("fed_len", _vp), ("n_spans", _vp), ("done", _vp), ("gen_count", _vp), ("control_bitmap", _vp),
                 ("max_len", _i), ("max_span", _i), ("out_token", _vp), ("out_probs", _vp)]
 
 
@@ -67,11 +67,11 @@ _SIGS = {
     "smer_attn_bwd_tc": (_i, [C.POINTER(AttnArgs), _vp]),
     "smer_attn_weights": (_i, [C.POINTER(AttnArgs), _vp, _ll, _vp]),
     "smer_xent_fwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _vp]),
-    "smer_xent_bwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _vp]),
+    "smer_xent_bwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _vp, _vp]),
     "smer_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _f, _f, _f, _f, _vp]),
     "smer_decode_attn_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "smer_decode_attn": (_i, [C.POINTER(DecodeAttnArgs), _vp]),
-    "smer_decode_gather": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "smer_decode_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "smer_embed_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "smer_sample_masked": (_i, [C.POINTER(SampleArgs), _vp]),
     "smer_cast2d": (_i, [_vp, _i, _ll, _vp, _i, _ll, _ll, _i, _i, _vp]),

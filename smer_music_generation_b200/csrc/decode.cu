@@ -176,19 +176,22 @@ extern "C" int smer_decode_attn(const smer_decode_attn_args* a, void* stream) {
 // token; their results are ignored by the sampler).
 // ---------------------------------------------------------------------------------------
 __global__ void decode_gather_kernel(const long long* __restrict__ tok_buf, const int* __restrict__ cur_len,
-                                     long long* __restrict__ ids, int* __restrict__ pos, int n, int max_len) {
+                                     const int* __restrict__ fed_len, long long* __restrict__ ids,
+                                     int* __restrict__ pos, int n, int max_len) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   int p = cur_len[s] - 1;
+  if (fed_len) p = min(p, fed_len[s]);
   p = p < 0 ? 0 : (p >= max_len ? max_len - 1 : p);
   ids[s] = tok_buf[(long long)s * max_len + p];
   pos[s] = p;
 }
 
-extern "C" int smer_decode_gather(const int64_t* tok_buf, const int* cur_len, int64_t* ids, int* pos, int n_seq,
-                                  int max_len, void* stream) {
+extern "C" int smer_decode_gather(const int64_t* tok_buf, const int* cur_len, const int* fed_len, int64_t* ids,
+                                  int* pos, int n_seq, int max_len, void* stream) {
   decode_gather_kernel<<<(n_seq + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const long long*)tok_buf, cur_len,
-                                                                               (long long*)ids, pos, n_seq, max_len);
+                                                                               fed_len, (long long*)ids, pos, n_seq,
+                                                                               max_len);
   SMER_CHECK_LAUNCH("smer_decode_gather");
   return SMER_OK;
 }

@@ -82,6 +82,15 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
   const int V = a.V;
   int st = a.state ? a.state[s] : 0;
   int pos = a.cur_len ? a.cur_len[s] - 1 : 0;                 // position of the token just fed
+  if (a.fed_len) {
+    // catch-up step: after a control token the stream grows by two (the token and the next span's
+    // m_0, generation.py:673-686); the first of them is fed without sampling.
+    int fed = a.fed_len[s];
+    if (fed < pos) {
+      if (tid == 0) a.fed_len[s] = fed + 1;
+      return;
+    }
+  }
   bool first = a.span_start ? (pos == a.span_start[s]) : false;
   int target = 0;
   if (a.targets) target = a.targets[(long long)s * a.max_spans + a.span_idx[s]];
@@ -220,6 +229,7 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
       }
       a.cur_len[s] = len;
       a.gen_count[s] = gen;
+      if (a.fed_len && !a.done[s]) a.fed_len[s] = pos + 1;
     }
     if (a.state) a.state[s] = st;
   }

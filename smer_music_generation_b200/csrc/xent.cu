@@ -46,10 +46,12 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 xent_bwd_kernel(const float* __restrict__ logits, long long ld, const int64_t* __restrict__ tgt,
                 const float* __restrict__ W, const float* __restrict__ lse, const double* __restrict__ sums,
-                T* __restrict__ dlogits, long long ldo, long long rows, int V, int Vpad, float gscale) {
+                T* __restrict__ dlogits, long long ldo, long long rows, int V, int Vpad, float gscale,
+                const float* __restrict__ gscale_dev) {
   int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  if (gscale_dev) gscale *= *gscale_dev;      // upstream d(loss) kept on the device (no host sync)
   float inv_denom = (float)(1.0 / sums[1]);
   for (long long r = warp; r < rows; r += nwarps) {
     long long y = tgt[r];
@@ -86,7 +88,8 @@ extern "C" int smer_xent_fwd(const float* logits, long long ld, const int64_t* t
 
 extern "C" int smer_xent_bwd(const float* logits, long long ld, const int64_t* targets, const float* W,
                              const float* lse, const double* sums, void* dlogits, int out_dtype, long long ldo,
-                             long long rows, int V, int Vpad, float grad_scale, void* stream) {
+                             long long rows, int V, int Vpad, float grad_scale, const float* grad_scale_dev,
+                             void* stream) {
   SMER_CHECK_ARG(Vpad >= V && ldo >= Vpad, "smer_xent_bwd: bad padding");
   if (rows == 0) return SMER_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -94,9 +97,9 @@ extern "C" int smer_xent_bwd(const float* logits, long long ld, const int64_t* t
   long long cap = (long long)smer_num_sms() * 8;
   int grid = (int)(blocks < cap ? blocks : cap);
   if (out_dtype == SMER_DT_F32)
-    xent_bwd_kernel<float><<<grid, 256, 0, st>>>(logits, ld, targets, W, lse, sums, (float*)dlogits, ldo, rows, V, Vpad, grad_scale);
+    xent_bwd_kernel<float><<<grid, 256, 0, st>>>(logits, ld, targets, W, lse, sums, (float*)dlogits, ldo, rows, V, Vpad, grad_scale, grad_scale_dev);
   else
-    xent_bwd_kernel<bf16><<<grid, 256, 0, st>>>(logits, ld, targets, W, lse, sums, (bf16*)dlogits, ldo, rows, V, Vpad, grad_scale);
+    xent_bwd_kernel<bf16><<<grid, 256, 0, st>>>(logits, ld, targets, W, lse, sums, (bf16*)dlogits, ldo, rows, V, Vpad, grad_scale, grad_scale_dev);
   SMER_CHECK_LAUNCH("smer_xent_bwd");
   return SMER_OK;
 }

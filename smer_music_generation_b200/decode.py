@@ -1,0 +1,378 @@
+"""KV-cached infilling decode (K12).
+
+The reference has no cache: generation.model_generate (generation.py:209-225) re-runs the
+whole encoder and decoder for every token.  Two entry points replace that arithmetic:
+
+* `cached_forward` -- sits *inside* ScoreTransformer.forward for the call shape model_generate
+  makes (batch 1, no padding masks, nopeek mask, eval mode).  The module remembers the piece
+  (encoder memory, per-layer cross K/V) and the decoder prefix (per-layer self K/V, logits
+  rows); a call whose `tgt` extends the cached prefix computes only the new positions, a
+  diverging `tgt` (span regeneration, evaluation.py:1303-1335) truncates the cache first.
+  generation.py therefore runs unchanged and gets the same (T,V) logits.
+* `InfillDecoder` -- batched generation of many independent pieces entirely on the device:
+  per step gather -> embed -> decoder layers (KV append + attention over the caches) -> fc ->
+  grammar-masked sampling + span bookkeeping (csrc/sample.cu), no host round trip per token.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi as K
+from . import ops
+
+TARGET_CODES = {"r": 0, "d": 1, "o": 2, "p": 3, "t": 4}
+
+
+# ----------------------------------------------------------------------------------------
+# shared: encoder + per-layer cross K/V
+# ----------------------------------------------------------------------------------------
+def _encode(model, src, src_pad):
+    """Runs the encoder stack; returns (mem (B*S,d), run)."""
+    from .model import _Run
+    B, S = src.shape
+    dummy_tgt = src[:, :1]
+    run = _Run(model, src, dummy_tgt, src_pad, None, src_pad, False, None, False, 0, False)
+    mem = run.encode(save=False)
+    return mem, run
+
+
+def _cross_kv(model, run, mem):
+    d = model.d_model
+    out = []
+    for i, layer in enumerate(model.transformer.decoder.layers):
+        ap = model._attn_p(layer.multihead_attn, f"transformer.decoder.layers.{i}.multihead_attn.")
+        kv = torch.empty(mem.shape[0], 2 * d, dtype=model.compute_dtype, device=mem.device)
+        ops.gemm_nt(mem, ap.w[d:3 * d], kv, bias=ap.b[d:])
+        out.append(kv)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# drop-in incremental forward (batch 1)
+# ----------------------------------------------------------------------------------------
+class _PieceCache:
+    def __init__(self, model, src):
+        self.src_cpu = src.detach().cpu()
+        self.S = src.shape[1]
+        dev = src.device
+        dt = model.compute_dtype
+        d = model.d_model
+        mem, run = _encode(model, src, None)
+        self.cross = _cross_kv(model, run, mem)
+        self.cap = 0
+        self.self_kv: List[torch.Tensor] = []
+        self.logits = None
+        self.weights = None
+        self.tokens: List[int] = []
+        self.dev, self.dt, self.d = dev, dt, d
+        self.nl = len(model.transformer.decoder.layers)
+        self.V = model.vocab_size
+        self.vpad = model.vpad
+
+    def reserve(self, T: int, want_w: bool):
+        if T > self.cap:
+            cap = max(256, 1 << (T - 1).bit_length())
+            old_kv, old_lg, old_w, n = self.self_kv, self.logits, self.weights, len(self.tokens)
+            self.self_kv = [torch.empty(cap, 2 * self.d, dtype=self.dt, device=self.dev) for _ in range(self.nl)]
+            self.logits = torch.empty(cap, self.vpad, dtype=torch.float32, device=self.dev)
+            self.weights = torch.zeros(self.nl, cap, self.S, dtype=torch.float32, device=self.dev) if want_w else None
+            if n:
+                for a, b in zip(self.self_kv, old_kv):
+                    a[:n].copy_(b[:n])
+                self.logits[:n].copy_(old_lg[:n])
+                if want_w and old_w is not None:
+                    self.weights[:, :n].copy_(old_w[:, :n])
+            self.cap = cap
+        if want_w and self.weights is None:
+            self.weights = torch.zeros(self.nl, self.cap, self.S, dtype=torch.float32, device=self.dev)
+            self.tokens = []                      # rows for the cached prefix were never computed
+
+
+def cached_forward(model, src, tgt, want_w: bool):
+    """ScoreTransformer.forward for (1,S)/(1,T) inputs with the nopeek mask (generation.py:217)."""
+    dev = src.device
+    pc: Optional[_PieceCache] = model._decode_cache
+    src_cpu = src.detach().cpu()
+    if pc is None or pc.dt != model.compute_dtype or pc.S != src.shape[1] or not torch.equal(pc.src_cpu, src_cpu):
+        pc = _PieceCache(model, src)
+        model._decode_cache = pc
+    toks = tgt[0].tolist()
+    T = len(toks)
+    pc.reserve(T, want_w)
+    P = 0
+    lim = min(len(pc.tokens), T)
+    while P < lim and pc.tokens[P] == toks[P]:
+        P += 1
+    if P < T:
+        _extend(model, pc, tgt, P, T, want_w)
+    pc.tokens = toks
+    V = model.vocab_size
+    logits = pc.logits[:T, :V].unsqueeze(0)
+    nl = pc.nl
+    if want_w:
+        weights = pc.weights[:, :T].unsqueeze(0)                       # (1,Ld,T,S)
+    else:
+        weights = torch.zeros((), device=dev).expand(1, nl, T, pc.S)
+    return logits, weights
+
+
+def _extend(model, pc: _PieceCache, tgt, P: int, T: int, want_w: bool):
+    """Computes decoder positions P..T-1 against the cached keys 0..P-1."""
+    d, H, ff = model.d_model, model.nhead, model.dim_feedforward
+    dh = d // H
+    dt, dev = pc.dt, pc.dev
+    k = T - P
+
+    def new(r, c, dtype=None):
+        return torch.empty(r, c, dtype=dtype or dt, device=dev)
+
+    def ln(branch, resid, w, b):
+        y = new(branch.shape[0], d)
+        z = new(branch.shape[0], d) if resid is not None else None
+        ops.layernorm_fwd(branch, resid, w, b, z, y, None, None)
+        return y
+
+    pe = model.pos_enc.pe.view(-1, d)
+    y = new(k, d)
+    ops.embed_pe(tgt[:, P:T].contiguous(), model.embedding.weight.detach(), pe, y, math.sqrt(d), P)
+    for i, layer in enumerate(model.transformer.decoder.layers):
+        lp = model._layer_p(layer, f"transformer.decoder.layers.{i}.")
+        sa, ca = lp.sa, lp.ca
+        q = new(k, d)
+        ops.gemm_nt(y, sa.w[:d], q, bias=sa.b[:d])
+        kv = pc.self_kv[i]
+        ops.gemm_nt(y, sa.w[d:3 * d], kv[P:T], bias=sa.b[d:])          # KV-cache append
+        o = new(k, d)
+        a = ops.attn_args(q, kv[:T, :d], kv[:T, d:], o, 1, H, k, T, dh, causal=True, q_pos0=P)
+        ops.attn_fwd(a)
+        proj = new(k, d)
+        ops.gemm_nt(o, sa.wo, proj, bias=sa.bo)
+        y1 = ln(proj, y, *lp.ln[0])
+        q2 = new(k, d)
+        ops.gemm_nt(y1, ca.w[:d], q2, bias=ca.b[:d])
+        ckv = pc.cross[i]
+        o2 = new(k, d)
+        lse = torch.empty(1, H, k, dtype=torch.float32, device=dev) if want_w else None
+        a2 = ops.attn_args(q2, ckv[:, :d], ckv[:, d:], o2, 1, H, k, pc.S, dh, lse=lse)
+        ops.attn_fwd(a2)
+        if want_w:
+            ops.attn_weights(a2, pc.weights[i, P:T])
+        proj2 = new(k, d)
+        ops.gemm_nt(o2, ca.wo, proj2, bias=ca.bo)
+        y2 = ln(proj2, y1, *lp.ln[1])
+        h = new(k, ff)
+        ops.gemm_nt(y2, lp.w1, h, bias=lp.b1, flags=K.EPI_RELU)
+        f = new(k, d)
+        ops.gemm_nt(h, lp.w2, f, bias=lp.b2)
+        y = ln(f, y2, *lp.ln[2])
+    dn = model.transformer.decoder.norm
+    yo = ln(y, None, dn.weight.detach(), dn.bias.detach())
+    wfc, bfc = model._fc_p()
+    ops.gemm_nt(yo, wfc, pc.logits[P:T], bias=bfc)
+
+
+# ----------------------------------------------------------------------------------------
+# batched on-device infilling
+# ----------------------------------------------------------------------------------------
+class InfillDecoder:
+    """Generates the infill spans of many independent pieces (BASELINE config 4).
+
+    pieces: list of 1-D int arrays -- the masked source sequences (output of
+            generation.mask_bar_and_track), one `m_0` per span.
+    targets: list of span-type strings per piece ('r','d','o','p','t'; generation.py:485-492).
+    The per-token arithmetic is that of generation_all's loop (generation.py:528-687) with the
+    K/V of earlier positions cached instead of recomputed.
+    """
+
+    def __init__(self, model, *, mode: str = "greedy", temperature: float = 1.0, top_p: float = 0.9, top_k: int = 0,
+                 seed: int = 0, max_len: int = 1024, max_span: int = 100,
+                 all_controls: Sequence[int] = tuple(range(242, 308)), splits: int = 1, use_graph: bool = True):
+        K.require_cuda_device()
+        self.m = model
+        self.mode = {"greedy": K.SAMPLE_GREEDY, "multinomial": K.SAMPLE_MULTINOMIAL, "top_p": K.SAMPLE_TOP_P,
+                     "top_k": K.SAMPLE_TOP_K}[mode]
+        self.temperature, self.top_p, self.top_k = float(temperature), float(top_p), int(top_k)
+        self.seed, self.max_len, self.max_span = int(seed), int(max_len), int(max_span)
+        self.splits = int(splits)
+        self.use_graph = use_graph
+        bm = np.zeros(10, dtype=np.uint32)
+        for c in all_controls:
+            bm[c >> 5] |= np.uint32(1 << (c & 31))
+        self.control_bitmap_host = bm
+        self.steps_run = 0
+        self.kernel_launches = 0
+
+    # -- state ------------------------------------------------------------------------
+    def _setup(self, pieces, targets, nwd, seq_base):
+        m = self.m
+        dev = m.embedding.weight.device
+        n = len(pieces)
+        d, H = m.d_model, m.nhead
+        S = max(len(p) for p in pieces)
+        S = (S + 7) // 8 * 8
+        src = torch.zeros(n, S, dtype=torch.int64)
+        pad = torch.ones(n, S, dtype=torch.bool)
+        for i, p in enumerate(pieces):
+            t = torch.as_tensor(np.asarray(p), dtype=torch.int64)
+            src[i, : len(t)] = t
+            pad[i, : len(t)] = False
+        self.h2d_bytes = src.numel() * 8 + pad.numel()
+        src = src.pin_memory().to(dev, non_blocking=True)
+        pad_u8 = pad.to(torch.uint8).pin_memory().to(dev, non_blocking=True)
+        self.n, self.S, self.dev = n, S, dev
+        self.src_len = torch.tensor([len(p) for p in pieces], dtype=torch.int32).to(dev)
+        mem, run = _encode(m, src, pad_u8)
+        self.cross = _cross_kv(m, run, mem)
+        del mem, run
+        nl = len(m.transformer.decoder.layers)
+        dt = m.compute_dtype
+        L = self.max_len
+        self.self_kv = [torch.zeros(n, L, 2 * d, dtype=dt, device=dev) for _ in range(nl)]
+        max_spans = max(len(t) for t in targets)
+        tg = torch.zeros(n, max_spans, dtype=torch.int8)
+        for i, t in enumerate(targets):
+            tg[i, : len(t)] = torch.tensor([TARGET_CODES[c] for c in t], dtype=torch.int8)
+        self.max_spans = max_spans
+        self.targets = tg.to(dev)
+        self.n_spans = torch.tensor([len(t) for t in targets], dtype=torch.int32).to(dev)
+        self.nwd = torch.tensor([1 if x else 0 for x in nwd], dtype=torch.uint8).to(dev)
+        self.tok_buf = torch.zeros(n, L, dtype=torch.int64, device=dev)
+        self.tok_buf[:, 0] = 2                                     # every stream opens with m_0
+        self.cur_len = torch.ones(n, dtype=torch.int32, device=dev)
+        self.fed_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.span_start = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.span_idx = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.done = (self.n_spans == 0).to(torch.int32)
+        self.gen_count = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.state = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.bitmap = torch.from_numpy(self.control_bitmap_host.view(np.int32).copy()).to(dev)
+        self.ids = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.seq_base = seq_base
+        ws = K.lib().smer_decode_attn_workspace_bytes(n, H, d // H, self.splits)
+        self.ws = torch.empty(max(ws, 4) // 4, dtype=torch.float32, device=dev)
+        # static activation buffers (graph-capturable step)
+        ff = m.dim_feedforward
+        mk = lambda c, t=None: torch.empty(n, c, dtype=t or dt, device=dev)
+        self.buf = dict(x=mk(d), qkv=mk(3 * d), o=mk(d), proj=mk(d), y1=mk(d), z=mk(d), q2=mk(d), o2=mk(d), y2=mk(d),
+                        h=mk(ff), f=mk(d), y3=mk(d), yo=mk(d), logits=mk(m.vpad, torch.float32))
+        self.layer_p = [m._layer_p(l, f"transformer.decoder.layers.{i}.") for i, l in enumerate(m.transformer.decoder.layers)]
+        self.fc_p = m._fc_p()
+        self.graph = None
+
+    def _decode_attn(self, q, new_k, new_v, kc, vc, out, kv_len, key_pad, ld_cache, cache_stride, cache_len, ld_pad):
+        m = self.m
+        a = K.DecodeAttnArgs()
+        a.q, a.new_k, a.new_v = q.data_ptr(), ops._p(new_k), ops._p(new_v)
+        a.k_cache, a.v_cache, a.out = kc.data_ptr(), vc.data_ptr(), out.data_ptr()
+        a.kv_len, a.key_pad, a.workspace = kv_len.data_ptr(), ops._p(key_pad), self.ws.data_ptr()
+        a.ldq, a.ld_new, a.ldo = q.stride(0), (new_k.stride(0) if new_k is not None else 0), out.stride(0)
+        a.ld_cache, a.cache_stride, a.ld_pad = ld_cache, cache_stride, ld_pad
+        a.n_seq, a.H, a.dh, a.cache_len, a.splits = self.n, m.nhead, m.d_model // m.nhead, cache_len, self.splits
+        a.dtype = K.dt(q)
+        a.scale = 1.0 / math.sqrt(m.d_model // m.nhead)
+        K.check(K.lib().smer_decode_attn(C.byref(a), K.stream()), "decode_attn")
+
+    def _step(self, step_idx_base: int):
+        """One token for every unfinished piece.  All launches on the current stream; no sync."""
+        m, b = self.m, self.buf
+        d = m.d_model
+        n, L, S = self.n, self.max_len, self.S
+        lib = K.lib()
+        K.check(lib.smer_decode_gather(self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.fed_len.data_ptr(),
+                                       self.ids.data_ptr(), self.pos.data_ptr(), n, L, K.stream()), "decode_gather")
+        K.check(lib.smer_embed_step(self.ids.data_ptr(), self.pos.data_ptr(), m.embedding.weight.data_ptr(),
+                                    m.pos_enc.pe.data_ptr(), b["x"].data_ptr(), K.dt(b["x"]), n, d, m.vocab_size,
+                                    math.sqrt(d), K.stream()), "embed_step")
+        x = b["x"]
+        launches = 2
+        for i, lp in enumerate(self.layer_p):
+            sa, ca = lp.sa, lp.ca
+            qkv = b["qkv"]
+            ops.gemm_nt(x, sa.w, qkv, bias=sa.b)
+            kv = self.self_kv[i]
+            self._decode_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], kv[:, :, :d], kv[:, :, d:], b["o"], self.pos,
+                              None, 2 * d, L * 2 * d, L, 0)
+            ops.gemm_nt(b["o"], sa.wo, b["proj"], bias=sa.bo)
+            ops.layernorm_fwd(b["proj"], x, lp.ln[0][0], lp.ln[0][1], b["z"], b["y1"], None, None)
+            ops.gemm_nt(b["y1"], ca.w[:d], b["q2"], bias=ca.b[:d])
+            ckv = self.cross[i]
+            self._decode_attn(b["q2"], None, None, ckv[:, :d], ckv[:, d:], b["o2"], self.src_len, None, 2 * d,
+                              S * 2 * d, S, 0)
+            ops.gemm_nt(b["o2"], ca.wo, b["proj"], bias=ca.bo)
+            ops.layernorm_fwd(b["proj"], b["y1"], lp.ln[1][0], lp.ln[1][1], b["z"], b["y2"], None, None)
+            ops.gemm_nt(b["y2"], lp.w1, b["h"], bias=lp.b1, flags=K.EPI_RELU)
+            ops.gemm_nt(b["h"], lp.w2, b["f"], bias=lp.b2)
+            ops.layernorm_fwd(b["f"], b["y2"], lp.ln[2][0], lp.ln[2][1], b["z"], b["y3"], None, None)
+            x = b["y3"]
+            launches += 11 + (2 if self.splits > 1 else 0)
+        dn = m.transformer.decoder.norm
+        ops.layernorm_fwd(x, None, dn.weight.detach(), dn.bias.detach(), None, b["yo"], None, None)
+        ops.gemm_nt(b["yo"], self.fc_p[0], b["logits"], bias=self.fc_p[1])
+        a = K.SampleArgs()
+        a.logits, a.ld, a.n_seq, a.V = b["logits"].data_ptr(), b["logits"].stride(0), n, m.vocab_size
+        a.mode, a.temperature, a.top_p, a.top_k = self.mode, self.temperature, self.top_p, self.top_k
+        a.seed, a.seq_base, a.step_base = self.seed, self.seq_base, 0
+        a.state, a.targets, a.nwd, a.max_spans = self.state.data_ptr(), self.targets.data_ptr(), self.nwd.data_ptr(), self.max_spans
+        a.raw_flags = a.raw_only_lo = a.raw_only_hi = None
+        a.tok_buf, a.cur_len, a.span_start = self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.span_start.data_ptr()
+        a.span_idx, a.fed_len, a.n_spans = self.span_idx.data_ptr(), self.fed_len.data_ptr(), self.n_spans.data_ptr()
+        a.done, a.gen_count, a.control_bitmap = self.done.data_ptr(), self.gen_count.data_ptr(), self.bitmap.data_ptr()
+        a.max_len, a.max_span = L, self.max_span
+        a.out_token = a.out_probs = None
+        K.check(lib.smer_sample_masked(C.byref(a), K.stream()), "sample_masked")
+        self.launches_per_step = launches + 3
+
+    # -- public -----------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, pieces, targets, nwd: Optional[Sequence[bool]] = None, seq_base: int = 0, max_steps: int = 0,
+                 check_every: int = 16) -> Dict[str, object]:
+        if self.m.training:
+            raise RuntimeError("InfillDecoder needs model.eval()")
+        n = len(pieces)
+        nwd = list(nwd) if nwd is not None else [False] * n
+        self._setup(pieces, targets, nwd, seq_base)
+        max_steps = max_steps or self.max_len
+        steps = 0
+        if self.use_graph:
+            # warm up once on a side stream (lazy module loads are not capturable), restore the state
+            snap = [t.clone() for t in (self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx,
+                                        self.done, self.gen_count, self.state)]
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._step(0)
+            torch.cuda.current_stream().wait_stream(s)
+            for t, c in zip((self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx, self.done,
+                             self.gen_count, self.state), snap):
+                t.copy_(c)
+            for kv in self.self_kv:
+                pass                                   # row 0 is rewritten by the first real step
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step(0)
+            for t, c in zip((self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx, self.done,
+                             self.gen_count, self.state), snap):
+                t.copy_(c)
+        while steps < max_steps:
+            for _ in range(check_every):
+                if self.graph is not None:
+                    self.graph.replay()
+                else:
+                    self._step(steps)
+                steps += 1
+            if bool(self.done.all().item()):           # one small D2H every `check_every` tokens
+                break
+        self.steps_run = steps
+        self.kernel_launches = steps * self.launches_per_step
+        tok = self.tok_buf.cpu()
+        lens = self.cur_len.cpu()
+        gen = self.gen_count.cpu()
+        self.d2h_bytes = tok.numel() * 8 + lens.numel() * 4 + gen.numel() * 4
+        streams = [tok[i, : int(lens[i])].tolist() for i in range(n)]
+        return {"streams": streams, "generated": gen.tolist(), "steps": steps, "done": self.done.cpu().tolist()}

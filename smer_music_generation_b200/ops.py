@@ -167,11 +167,11 @@ def xent_fwd(logits, targets, W, Cw, category, ncat, lse, sums, V):
                                   _p(lse), _p(sums), rows, V, K.stream()), "xent_fwd")
 
 
-def xent_bwd(logits, targets, W, lse, sums, dlogits, V, grad_scale=1.0):
+def xent_bwd(logits, targets, W, lse, sums, dlogits, V, grad_scale=1.0, grad_scale_dev=None):
     rows = logits.shape[0]
     K.check(K.lib().smer_xent_bwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(lse), _p(sums), _p(dlogits),
                                   K.dt(dlogits), dlogits.stride(0), rows, V, dlogits.shape[1], grad_scale,
-                                  K.stream()), "xent_bwd")
+                                  _p(grad_scale_dev), K.stream()), "xent_bwd")
 
 
 def adam_step(p, g, m, v, shadow, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
