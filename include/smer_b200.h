@@ -151,7 +151,7 @@ typedef struct smer_sample_args {
   long long ld;
   int n_seq, V;
   int mode;                   /* SMER_SAMPLE_*                                                */
-  float temperature, top_p;
+  double temperature, top_p;  /* doubles: the reference divides float64 logits by a Python float */
   int top_k;
   uint64_t seed;              /* Philox key; counter = (seq_base+s, step, draw)               */
   long long seq_base;

@@ -40,8 +40,8 @@ class DecodeAttnArgs(C.Structure):
 
 
 class SampleArgs(C.Structure):
-    _fields_ = [("logits", _vp), ("ld", _ll), ("n_seq", _i), ("V", _i), ("mode", _i), ("temperature", _f),
-                ("top_p", _f), ("top_k", _i), ("seed", _u64), ("seq_base", _ll), ("step_base", _u64),
+    _fields_ = [("logits", _vp), ("ld", _ll), ("n_seq", _i), ("V", _i), ("mode", _i), ("temperature", C.c_double),
+                ("top_p", C.c_double), ("top_k", _i), ("seed", _u64), ("seq_base", _ll), ("step_base", _u64),
                 ("state", _vp), ("targets", _vp), ("nwd", _vp), ("max_spans", _i), ("raw_flags", _vp),
                 ("raw_only_lo", _vp), ("raw_only_hi", _vp), ("tok_buf", _vp), ("cur_len", _vp), ("span_start", _vp),
                 ("span_idx", _vp), ("fed_len", _vp), ("n_spans", _vp), ("done", _vp), ("gen_count", _vp), ("control_bitmap", _vp),

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
                                     a.raw_only_hi ? a.raw_only_hi[s] : -1, 0}
                           : flags_for(st, first, target, nwd);
   const float* x = a.logits + (long long)s * a.ld;
-  double t = (double)a.temperature;
+  double t = a.temperature;
   // masked softmax in float64, no max shift (generation.py:28-30)
   double part = 0.0;
   for (int i = tid; i < V; i += 128) {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
         double cs = 0.0;
         for (int r = 0; r < V; ++r) {
           cs += q[order[r]];
-          if (cs > (double)a.top_p) { keep = r + 1; break; }
+          if (cs > a.top_p) { keep = r + 1; break; }
         }
       } else {
         keep = a.top_k < 1 ? 1 : (a.top_k > V ? V : a.top_k);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
 extern "C" int smer_sample_masked(const smer_sample_args* a, void* stream) {
   SMER_CHECK_ARG(a && a->logits && a->n_seq > 0, "smer_sample_masked: null args");
   SMER_CHECK_ARG(a->V > 0 && a->V <= VMAX, "smer_sample_masked: V=%d exceeds %d", a->V, VMAX);
-  SMER_CHECK_ARG(a->temperature > 0.f, "smer_sample_masked: temperature must be positive");
+  SMER_CHECK_ARG(a->temperature > 0.0, "smer_sample_masked: temperature must be positive");
   SMER_CHECK_ARG(!a->tok_buf || (a->cur_len && a->span_start && a->span_idx && a->n_spans && a->done && a->gen_count),
                  "smer_sample_masked: stream bookkeeping needs cur_len/span_start/span_idx/n_spans/done/gen_count");
   sample_kernel<<<a->n_seq, 128, 0, (cudaStream_t)stream>>>(*a);

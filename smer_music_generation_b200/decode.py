@@ -98,8 +98,11 @@ def cached_forward(model, src, tgt, want_w: bool):
     dev = src.device
     pc: Optional[_PieceCache] = model._decode_cache
     src_cpu = src.detach().cpu()
-    if pc is None or pc.dt != model.compute_dtype or pc.S != src.shape[1] or not torch.equal(pc.src_cpu, src_cpu):
+    stamp = sum(p._version for p in model.parameters())        # weights changed in place -> cache is stale
+    if (pc is None or pc.dt != model.compute_dtype or pc.S != src.shape[1] or pc.stamp != stamp
+            or not torch.equal(pc.src_cpu, src_cpu)):
         pc = _PieceCache(model, src)
+        pc.stamp = stamp
         model._decode_cache = pc
     toks = tgt[0].tolist()
     T = len(toks)
@@ -133,8 +136,7 @@ def _extend(model, pc: _PieceCache, tgt, P: int, T: int, want_w: bool):
 
     def ln(branch, resid, w, b):
         y = new(branch.shape[0], d)
-        z = new(branch.shape[0], d) if resid is not None else None
-        ops.layernorm_fwd(branch, resid, w, b, z, y, None, None)
+        ops.layernorm_fwd(branch, resid, w, b, None, y, None, None)
         return y
 
     pe = model.pos_enc.pe.view(-1, d)

@@ -138,10 +138,13 @@ class _Weights:
         self.model = model
         self._shadow: Dict[str, torch.Tensor] = {}
         self._key: Dict[str, Tuple[int, int]] = {}
+        self.external: Dict[str, torch.Tensor] = {}      # shadows owned by trainer.ParamArena
 
     def mat(self, name: str, p: torch.Tensor, rows_pad: int = 0) -> torch.Tensor:
         if self.model.compute_dtype == torch.float32:
             return p.detach()
+        if name in self.external:
+            return self.external[name]
         key = (p.data_ptr(), p._version)
         sh = self._shadow.get(name)
         if sh is None or self._key.get(name) != key or sh.device != p.device:
@@ -156,6 +159,8 @@ class _Weights:
     def vec(self, name: str, p: torch.Tensor, pad: int = 0) -> torch.Tensor:
         if pad <= p.shape[0]:
             return p.detach()
+        if name in self.external:
+            return self.external[name]
         key = (p.data_ptr(), p._version)
         sh = self._shadow.get(name)
         if sh is None or self._key.get(name) != key or sh.device != p.device:

@@ -15,6 +15,32 @@ _TC_GEMM = os.environ.get("SMER_GEMM", "tc")     # "simt" forces the CUDA-core G
 _TC_ATTN = os.environ.get("SMER_ATTN", "tc")
 _NUM_SMS = None
 
+# ---- optional per-kernel-family timing (bench.py): events on the launching stream ------------
+PROFILE = None           # None or dict label -> list[(start_event, end_event, work)]
+LAUNCHES = 0             # kernels launched through this module (counted, not estimated)
+
+
+class _Timed:
+    __slots__ = ("label", "work", "n", "s")
+
+    def __init__(self, label, work=0.0, n=1):
+        self.label, self.work, self.n = label, work, n
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.n
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream())
+            PROFILE.setdefault(self.label, []).append((self.s, e, self.work))
+        return False
+
 
 def num_sms() -> int:
     global _NUM_SMS
@@ -28,31 +54,35 @@ def _p(t):
 
 
 def embed_pe(ids, emb, pe, out, scale, pos0=0, dropout_p=0.0, seed=0, site=0):
-    B, L = ids.shape
-    V, d = emb.shape
-    K.check(K.lib().smer_embed_pe_fwd(_p(ids), _p(emb), _p(pe), _p(out), K.dt(out), B, L, d, V, pos0, scale,
-                                      dropout_p, seed, site, K.stream()), "embed_pe_fwd")
+    with _Timed("embed", float(ids.numel() * emb.shape[1] * (4 + out.element_size())), 1):
+        B, L = ids.shape
+        V, d = emb.shape
+        K.check(K.lib().smer_embed_pe_fwd(_p(ids), _p(emb), _p(pe), _p(out), K.dt(out), B, L, d, V, pos0, scale,
+                                          dropout_p, seed, site, K.stream()), "embed_pe_fwd")
 
 
 def embed_bwd(ids, dout, demb, scale, dropout_p=0.0, seed=0, site=0):
-    B, L = ids.shape
-    V, d = demb.shape
-    K.check(K.lib().smer_embed_bwd(_p(ids), _p(dout), K.dt(dout), _p(demb), B, L, d, V, scale, dropout_p, seed,
-                                   site, K.stream()), "embed_bwd")
+    with _Timed("embed_bwd", float(ids.numel() * demb.shape[1] * (4 + dout.element_size())), 1):
+        B, L = ids.shape
+        V, d = demb.shape
+        K.check(K.lib().smer_embed_bwd(_p(ids), _p(dout), K.dt(dout), _p(demb), B, L, d, V, scale, dropout_p, seed,
+                                       site, K.stream()), "embed_bwd")
 
 
 def layernorm_fwd(branch, resid, gamma, beta, z_out, y, mean, rstd, eps=1e-5, dropout_p=0.0, seed=0, site=0):
-    rows, d = branch.shape
-    K.check(K.lib().smer_layernorm_fwd(_p(branch), _p(resid), _p(gamma), _p(beta), _p(z_out), _p(y), _p(mean),
-                                       _p(rstd), K.dt(branch), rows, d, eps, dropout_p, seed, site, K.stream()),
-            "layernorm_fwd")
+    with _Timed("layernorm_fwd", float(branch.numel() * branch.element_size() * (2 + (resid is not None) + (z_out is not None))), 1):
+        rows, d = branch.shape
+        K.check(K.lib().smer_layernorm_fwd(_p(branch), _p(resid), _p(gamma), _p(beta), _p(z_out), _p(y), _p(mean),
+                                           _p(rstd), K.dt(branch), rows, d, eps, dropout_p, seed, site, K.stream()),
+                "layernorm_fwd")
 
 
 def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dropout_p=0.0, seed=0, site=0):
-    rows, d = dy.shape
-    K.check(K.lib().smer_layernorm_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dbranch),
-                                       _p(dgamma), _p(dbeta), K.dt(dy), rows, d, dropout_p, seed, site, K.stream()),
-            "layernorm_bwd")
+    with _Timed("layernorm_bwd", float(dy.numel() * dy.element_size() * (3 + (dbranch is not None))), 1):
+        rows, d = dy.shape
+        K.check(K.lib().smer_layernorm_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dbranch),
+                                           _p(dgamma), _p(dbeta), K.dt(dy), rows, d, dropout_p, seed, site, K.stream()),
+                "layernorm_bwd")
 
 
 def _tc_ok(a_dtype, N, ldc, *pitches):
@@ -62,53 +92,57 @@ def _tc_ok(a_dtype, N, ldc, *pitches):
 
 def gemm_nt(A, W, out, bias=None, resid=None, flags=0, dropout_p=0.0, seed=0, site=0):
     """out[M,N] = epi(A[M,K] @ W[N,K]^T) -- nn.Linear forward.  A/out may be strided row views."""
-    M, Kd = A.shape
-    N = W.shape[0]
-    lda, ldw, ldc = A.stride(0), W.stride(0), out.stride(0)
-    ldr = resid.stride(0) if resid is not None else 0
-    if _tc_ok(A.dtype, N, ldc, lda, ldw):
-        K.check(K.lib().smer_gemm_bf16_tc(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(out), M, N, Kd, _p(bias),
-                                          _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()), "gemm_tc(nt)")
-    else:
-        K.check(K.lib().smer_gemm_simt(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(A), K.dt(out), M, N, Kd,
-                                       _p(bias), _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()),
-                "gemm_simt(nt)")
+    with _Timed("gemm", 2.0 * A.shape[0] * A.shape[1] * W.shape[0], 1):
+        M, Kd = A.shape
+        N = W.shape[0]
+        lda, ldw, ldc = A.stride(0), W.stride(0), out.stride(0)
+        ldr = resid.stride(0) if resid is not None else 0
+        if _tc_ok(A.dtype, N, ldc, lda, ldw):
+            K.check(K.lib().smer_gemm_bf16_tc(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(out), M, N, Kd, _p(bias),
+                                              _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()), "gemm_tc(nt)")
+        else:
+            K.check(K.lib().smer_gemm_simt(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(A), K.dt(out), M, N, Kd,
+                                           _p(bias), _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()),
+                    "gemm_simt(nt)")
 
 
 def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0):
     """out[M,Kin] = epi(dY[M,N] @ W[N,Kin]) -- input gradient of nn.Linear."""
-    M, N = dY.shape
-    Kin = W.shape[1]
-    ldy, ldw, ldc = dY.stride(0), W.stride(0), out.stride(0)
-    ldr = resid.stride(0) if resid is not None else 0
-    if _tc_ok(dY.dtype, Kin, ldc, ldy, ldw):
-        K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 1, _p(W), ldw, 0, _p(out), ldc, K.dt(out), M, Kin, N, 0,
-                                          _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_tc(dx)")
-    else:
-        K.check(K.lib().smer_gemm_simt(_p(dY), ldy, 1, _p(W), 1, ldw, _p(out), ldc, K.dt(dY), K.dt(out), M, Kin, N,
-                                       0, _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_simt(dx)")
+    with _Timed("gemm", 2.0 * dY.shape[0] * dY.shape[1] * W.shape[1], 1):
+        M, N = dY.shape
+        Kin = W.shape[1]
+        ldy, ldw, ldc = dY.stride(0), W.stride(0), out.stride(0)
+        ldr = resid.stride(0) if resid is not None else 0
+        if _tc_ok(dY.dtype, Kin, ldc, ldy, ldw):
+            K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 1, _p(W), ldw, 0, _p(out), ldc, K.dt(out), M, Kin, N, 0,
+                                              _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_tc(dx)")
+        else:
+            K.check(K.lib().smer_gemm_simt(_p(dY), ldy, 1, _p(W), 1, ldw, _p(out), ldc, K.dt(dY), K.dt(out), M, Kin, N,
+                                           0, _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_simt(dx)")
 
 
 def gemm_dw(dY, X, out):
     """out[N,Kin] += dY[M,N]^T @ X[M,Kin] (fp32, `out` pre-zeroed) -- weight gradient of nn.Linear."""
-    M, N = dY.shape
-    Kin = X.shape[1]
-    ldy, ldx, ldc = dY.stride(0), X.stride(0), out.stride(0)
-    if _tc_ok(dY.dtype, Kin, ldc, ldy, ldx):
-        tiles = ((N + 127) // 128) * ((Kin + 127) // 128)
-        split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
-        K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 0, _p(X), ldx, 0, _p(out), ldc, K.F32, N, Kin, M, 0, 0, 0,
-                                          K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_tc(dw)")
-    else:
-        tiles = ((N + 63) // 64) * ((Kin + 63) // 64)
-        split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
-        K.check(K.lib().smer_gemm_simt(_p(dY), 1, ldy, _p(X), 1, ldx, _p(out), ldc, K.dt(dY), K.F32, N, Kin, M, 0, 0,
-                                       0, K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_simt(dw)")
+    with _Timed("gemm_dw", 2.0 * dY.shape[0] * dY.shape[1] * X.shape[1], 1):
+        M, N = dY.shape
+        Kin = X.shape[1]
+        ldy, ldx, ldc = dY.stride(0), X.stride(0), out.stride(0)
+        if _tc_ok(dY.dtype, Kin, ldc, ldy, ldx):
+            tiles = ((N + 127) // 128) * ((Kin + 127) // 128)
+            split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
+            K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 0, _p(X), ldx, 0, _p(out), ldc, K.F32, N, Kin, M, 0, 0, 0,
+                                              K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_tc(dw)")
+        else:
+            tiles = ((N + 63) // 64) * ((Kin + 63) // 64)
+            split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
+            K.check(K.lib().smer_gemm_simt(_p(dY), 1, ldy, _p(X), 1, ldx, _p(out), ldc, K.dt(dY), K.F32, N, Kin, M, 0, 0,
+                                           0, K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_simt(dw)")
 
 
 def colsum(x, out):
-    rows, cols = x.shape
-    K.check(K.lib().smer_colsum(_p(x), K.dt(x), x.stride(0), _p(out), rows, cols, K.stream()), "colsum")
+    with _Timed("colsum", float(x.numel() * x.element_size()), 1):
+        rows, cols = x.shape
+        K.check(K.lib().smer_colsum(_p(x), K.dt(x), x.stride(0), _p(out), rows, cols, K.stream()), "colsum")
 
 
 def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0, key_pad=None, kv_len=None,
@@ -137,22 +171,31 @@ def _attn_tc_ok(a) -> bool:
     return _TC_ATTN == "tc" and a.dtype == K.BF16 and a.dh == 64 and not a.add_mask and a.q_pos0 == 0
 
 
+def _attn_flops(a):
+    """Algorithmic flops of one attention forward: 4*Lq*Lk*dh per (b,h); causal counts half."""
+    f = 4.0 * a.B * a.H * a.Lq * a.Lk * a.dh
+    return f * 0.5 if (a.causal and a.Lq == a.Lk) else f
+
+
 def attn_fwd(a):
-    if _attn_tc_ok(a) and ATTN_TC_FWD:
-        K.check(K.lib().smer_attn_fwd_tc(C.byref(a), K.stream()), "attn_fwd_tc")
-    else:
-        K.check(K.lib().smer_attn_fwd_simt(C.byref(a), K.stream()), "attn_fwd_simt")
+    with _Timed("attn_fwd", _attn_flops(a)):
+        if _attn_tc_ok(a) and ATTN_TC_FWD:
+            K.check(K.lib().smer_attn_fwd_tc(C.byref(a), K.stream()), "attn_fwd_tc")
+        else:
+            K.check(K.lib().smer_attn_fwd_simt(C.byref(a), K.stream()), "attn_fwd_simt")
 
 
 def attn_bwd(a):
-    if _attn_tc_ok(a) and ATTN_TC_BWD:
-        K.check(K.lib().smer_attn_bwd_tc(C.byref(a), K.stream()), "attn_bwd_tc")
-    else:
-        K.check(K.lib().smer_attn_bwd_simt(C.byref(a), K.stream()), "attn_bwd_simt")
+    with _Timed("attn_bwd", 2.0 * _attn_flops(a), 3):
+        if _attn_tc_ok(a) and ATTN_TC_BWD:
+            K.check(K.lib().smer_attn_bwd_tc(C.byref(a), K.stream()), "attn_bwd_tc")
+        else:
+            K.check(K.lib().smer_attn_bwd_simt(C.byref(a), K.stream()), "attn_bwd_simt")
 
 
 def attn_weights(a, w):
-    K.check(K.lib().smer_attn_weights(C.byref(a), _p(w), w.stride(-2), K.stream()), "attn_weights")
+    with _Timed("attn_weights"):
+        K.check(K.lib().smer_attn_weights(C.byref(a), _p(w), w.stride(-2), K.stream()), "attn_weights")
 
 
 # Which tcgen05 attention kernels this build provides (attn_tc.cu); the dispatcher above is a
@@ -162,39 +205,46 @@ ATTN_TC_BWD = False
 
 
 def xent_fwd(logits, targets, W, Cw, category, ncat, lse, sums, V):
-    rows = logits.shape[0]
-    K.check(K.lib().smer_xent_fwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(Cw), _p(category), ncat,
-                                  _p(lse), _p(sums), rows, V, K.stream()), "xent_fwd")
+    with _Timed("xent_fwd", float(logits.shape[0] * V * 4), 1):
+        rows = logits.shape[0]
+        K.check(K.lib().smer_xent_fwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(Cw), _p(category), ncat,
+                                      _p(lse), _p(sums), rows, V, K.stream()), "xent_fwd")
 
 
 def xent_bwd(logits, targets, W, lse, sums, dlogits, V, grad_scale=1.0, grad_scale_dev=None):
-    rows = logits.shape[0]
-    K.check(K.lib().smer_xent_bwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(lse), _p(sums), _p(dlogits),
-                                  K.dt(dlogits), dlogits.stride(0), rows, V, dlogits.shape[1], grad_scale,
-                                  _p(grad_scale_dev), K.stream()), "xent_bwd")
+    with _Timed("xent_bwd", float(logits.shape[0] * V * (4 + dlogits.element_size())), 1):
+        rows = logits.shape[0]
+        K.check(K.lib().smer_xent_bwd(_p(logits), logits.stride(0), _p(targets), _p(W), _p(lse), _p(sums), _p(dlogits),
+                                      K.dt(dlogits), dlogits.stride(0), rows, V, dlogits.shape[1], grad_scale,
+                                      _p(grad_scale_dev), K.stream()), "xent_bwd")
 
 
 def adam_step(p, g, m, v, shadow, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
-    K.check(K.lib().smer_adam_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), step, lr, b1, b2, eps,
-                                   grad_scale, K.stream()), "adam_step")
+    with _Timed("adam", float(p.numel() * (28 + (2 if shadow is not None else 0))), 1):
+        K.check(K.lib().smer_adam_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), step, lr, b1, b2, eps,
+                                       grad_scale, K.stream()), "adam_step")
 
 
 def cast2d(src, dst, cols=None):
-    rows = src.shape[0]
-    cols = src.shape[1] if cols is None else cols
-    K.check(K.lib().smer_cast2d(_p(src), K.dt(src), src.stride(0), _p(dst), K.dt(dst), dst.stride(0), rows, cols,
-                                dst.shape[1], K.stream()), "cast2d")
+    with _Timed("cast", 0.0, 1):
+        rows = src.shape[0]
+        cols = src.shape[1] if cols is None else cols
+        K.check(K.lib().smer_cast2d(_p(src), K.dt(src), src.stride(0), _p(dst), K.dt(dst), dst.stride(0), rows, cols,
+                                    dst.shape[1], K.stream()), "cast2d")
 
 
 def cast_f32_to_bf16(src, dst):
-    K.check(K.lib().smer_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), K.stream()), "cast_f32_to_bf16")
+    with _Timed("cast", float(src.numel() * 6), 1):
+        K.check(K.lib().smer_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), K.stream()), "cast_f32_to_bf16")
 
 
 def kv_len_from_pad(pad_u8, out):
-    B, L = pad_u8.shape
-    K.check(K.lib().smer_kv_len_from_pad(_p(pad_u8), _p(out), B, L, K.stream()), "kv_len_from_pad")
+    with _Timed("misc", 0.0, 1):
+        B, L = pad_u8.shape
+        K.check(K.lib().smer_kv_len_from_pad(_p(pad_u8), _p(out), B, L, K.stream()), "kv_len_from_pad")
 
 
 def classify_mask(mask2d, flags3):
-    T = mask2d.shape[0]
-    K.check(K.lib().smer_classify_mask(_p(mask2d), mask2d.stride(0), T, _p(flags3), K.stream()), "classify_mask")
+    with _Timed("misc", 0.0, 1):
+        T = mask2d.shape[0]
+        K.check(K.lib().smer_classify_mask(_p(mask2d), mask2d.stride(0), T, _p(flags3), K.stream()), "classify_mask")

@@ -1,0 +1,214 @@
+"""Teacher-forced training step of the reference (train.py:702-797) as one device-side pipeline:
+forward -> fused class-weighted cross-entropy -> backward -> Adam, with no host synchronisation
+inside the step, and data-parallel over N GPUs (one process per GPU).
+
+Data parallelism: every rank holds a replica; the batch is split across ranks.
+  * The loss normaliser sum_i C[y_i] (train.py:736) is batch-GLOBAL, so the 16 doubles the loss
+    kernel produces are all-reduced before the loss backward runs: gradients equal those of the
+    single-process step on the concatenated batch.
+  * Gradients live in one flat fp32 arena laid out in backward-completion order; as soon as a
+    group of layers has finished its backward, its contiguous slice is all-reduced (NCCL over
+    NVLink/NVSwitch) on a side stream while earlier layers' backward kernels keep running.
+  * Adam (train.py:264 defaults) is one fused launch over the parameter arena and refreshes the
+    bf16 weight shadows in the same pass.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _capi as K
+from . import ops
+from .loss import CATEGORIES, CONTROL_NAMES, loss_tables
+from .model import GradArena, ScoreTransformer, _Run
+
+
+class ParamArena:
+    """Re-homes the module's parameters into one flat fp32 buffer with GradArena's layout (the
+    Parameters stay the same objects, so state_dict / checkpoints are unchanged) and keeps flat
+    Adam moments and a flat bf16 shadow beside it."""
+
+    def __init__(self, model: ScoreTransformer):
+        self.layout = GradArena(model)
+        lay = self.layout
+        dev = lay.flat.device
+        self.flat = torch.zeros(lay.total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.shadow = torch.zeros(lay.total, dtype=torch.bfloat16, device=dev) if model.compute_dtype == torch.bfloat16 else None
+        params = dict(model.named_parameters())
+        ext: Dict[str, torch.Tensor] = {}
+        vpad = model.vpad
+        for n in lay.order:
+            p = params[n]
+            o, numel = lay.offsets[n]
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            if self.shadow is not None and p.dim() == 2 and n != "embedding.weight":
+                rows = vpad if n == "fc.weight" else p.shape[0]
+                ext[n] = self.shadow[o:o + rows * p.shape[1]].view(rows, p.shape[1])
+        if model.compute_dtype == torch.bfloat16:
+            o, numel = lay.offsets["fc.bias"]
+            ext["fc.bias"] = self.flat[o:o + vpad]
+        model._w.external = ext
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        if self.shadow is not None:
+            ops.cast_f32_to_bf16(self.flat, self.shadow)
+
+
+class TrainEngine:
+    def __init__(self, model: ScoreTransformer, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 eos_weight: float = 0.8, control_list: Sequence[str] = CONTROL_NAMES, process_group=None,
+                 n_buckets: int = 4):
+        K.require_cuda_device()
+        self.model = model
+        self.dev = model.embedding.weight.device
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.arena = ParamArena(model)
+        self.grads = self.arena.layout                      # GradArena: flat fp32 grads + views
+        model._grad_arena = self.grads
+        self.grads.vpad = model.vpad
+        W, C, cat = loss_tables(model.vocab_size, eos_weight, control_list)
+        self.W, self.C, self.cat = W.to(self.dev), C.to(self.dev), cat.to(self.dev)
+        self.ncat = len(CATEGORIES)
+        self.sums = torch.zeros(K.XENT_MAX_SUMS, dtype=torch.float64, device=self.dev)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        self._pending = []
+        self._bucket_bounds = self._make_buckets(n_buckets)
+        self._done_prefixes: List[str] = []
+        self.last_launches = 0
+
+    # ---- gradient buckets -------------------------------------------------------------
+    def _make_buckets(self, n: int):
+        """Splits the arena (already in backward-completion order) into ~n contiguous ranges
+        ending on layer boundaries; returns [(last_prefix_of_bucket, begin, end)]."""
+        m = self.model
+        groups = ["fc."]
+        nd, ne = len(m.transformer.decoder.layers), len(m.transformer.encoder.layers)
+        groups += [f"transformer.decoder.layers.{i}." for i in reversed(range(nd))]
+        groups += ["transformer.decoder.norm."]
+        groups += [f"transformer.encoder.layers.{i}." for i in reversed(range(ne))]
+        groups += ["transformer.encoder.norm.", "embedding."]
+        # completion order in _Run.backward: fc, dec layers (top-down), decoder.norm is signalled
+        # after the decoder loop, encoder layers, then encoder.norm + embedding at the very end.
+        spans = {g: self.grads.span(g) for g in groups}
+        self._spans = spans
+        per = max(1, math.ceil(len(groups) / max(1, n)))
+        buckets = []
+        for i in range(0, len(groups), per):
+            chunk = groups[i:i + per]
+            buckets.append((chunk, min(spans[g][0] for g in chunk), max(spans[g][1] for g in chunk)))
+        return buckets
+
+    def _grad_hook(self, prefix: str):
+        """Called by _Run.backward when every gradient of `prefix` has been written."""
+        import torch.distributed as dist
+        self._done_prefixes.append(prefix)
+        done = set(self._done_prefixes)
+        for chunk, b, e in self._bucket_bounds:
+            key = (b, e)
+            if key in self._launched or not all(g in done for g in chunk):
+                continue
+            self._launched.add(key)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                dist.all_reduce(self.grads.flat[b:e], op=dist.ReduceOp.SUM, group=self.pg)
+
+    # ---- one step ---------------------------------------------------------------------
+    def step(self, src, tgt_in, tgt_out, src_pad=None, tgt_pad=None, update: bool = True):
+        """All arguments are device tensors.  Returns the device tensor `sums` (fp64[16]):
+        sums[0]/sums[1] is the loss, sums[2+k]/sums[1] the k-th category term."""
+        m = self.model
+        if not m.training:
+            raise RuntimeError("TrainEngine.step needs model.train()")
+        B, S = src.shape
+        T = tgt_in.shape[1]
+        self.step_count += 1
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self.step_count * 0xD1342543DE82EF95
+                + (0 if self.pg is None else 7919 * torch.distributed.get_rank(self.pg))) & 0xFFFFFFFFFFFFFFFF
+        pad_s = None if src_pad is None else src_pad.to(torch.uint8)
+        pad_t = None if tgt_pad is None else tgt_pad.to(torch.uint8)
+        run = _Run(m, src, tgt_in, pad_s, pad_t, pad_s, True, None, True, seed, False)
+        logits = run.forward(save=True)                              # (B*T, vpad) fp32
+        V, vp = m.vocab_size, m.vpad
+        tg = tgt_out.reshape(-1)
+        lse = torch.empty(B * T, dtype=torch.float32, device=self.dev)
+        ops.xent_fwd(logits, tg, self.W, self.C, self.cat, self.ncat, lse, self.sums, V)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.pg)     # global normaliser
+        dl = torch.empty(B * T, vp, dtype=m.compute_dtype, device=self.dev)
+        ops.xent_bwd(logits, tg, self.W, lse, self.sums, dl, V, 1.0)
+        self.grads.flat.zero_()
+        if self.world > 1:
+            self._done_prefixes, self._launched = [], set()
+            m.grad_hook = self._grad_hook
+        try:
+            run.backward(dl, self.grads.views)
+        finally:
+            m.grad_hook = None
+        if self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if update:
+            self.adam()
+        return self.sums
+
+    def adam(self):
+        a = self.arena
+        ops.adam_step(a.flat, self.grads.flat, a.m, a.v, a.shadow, self.step_count, self.lr, self.betas[0],
+                      self.betas[1], self.eps, 1.0)
+
+    def loss_value(self) -> float:
+        s = self.sums.tolist()
+        return s[0] / s[1]
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr) semantics (train.py:264: default betas/eps, no weight decay,
+    no amsgrad) with the update done by csrc/elementwise.cu:adam_kernel, one launch per tensor.
+    For the module-API path (`loss.backward(); optim.step()`); TrainEngine uses the flat arena."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    n = (p.numel() + 3) // 4 * 4
+                    st["exp_avg"] = torch.zeros(n, dtype=torch.float32, device=p.device)
+                    st["exp_avg_sq"] = torch.zeros(n, dtype=torch.float32, device=p.device)
+                st["step"] += 1
+                if p.numel() % 4 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    # 309-element fc.bias: run on padded scratch copies
+                    n = st["exp_avg"].numel()
+                    pp = torch.zeros(n, device=p.device)
+                    gg = torch.zeros(n, device=p.device)
+                    pp[: p.numel()].copy_(p.reshape(-1))
+                    gg[: p.numel()].copy_(p.grad.reshape(-1))
+                    ops.adam_step(pp, gg, st["exp_avg"], st["exp_avg_sq"], None, st["step"], g["lr"], g["betas"][0],
+                                  g["betas"][1], g["eps"])
+                    p.copy_(pp[: p.numel()].view(p.shape))
+                else:
+                    ops.adam_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], None, st["step"], g["lr"],
+                                  g["betas"][0], g["betas"][1], g["eps"])
+        return loss

@@ -38,7 +38,7 @@ def test_state_dict_layout_matches_reference(golden_dir):
         assert torch.equal(mine[k].cpu(), v), k
 
 
-@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 1e-3), ("bf16", 2e-2, 8e-2)])
+@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 1e-3), ("bf16", 2e-2, 1.5e-1)])
 def test_forward_loss_grads_vs_reference(golden_dir, mode, tol, gtol):
     from smer_music_generation_b200 import SmerLoss
     g = _load(golden_dir, "fwd_small.pt")
@@ -69,6 +69,9 @@ def test_forward_loss_grads_vs_reference(golden_dir, mode, tol, gtol):
             e = (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
             worst = max(worst, e)
             assert e < gtol, (n, e)
+            if ref.numel() > 64:
+                cos = torch.nn.functional.cosine_similarity(p.grad.cpu().flatten(), ref.flatten(), dim=0).item()
+                assert cos > (0.9999 if mode == "fp32" else 0.995), (n, cos)
     # torch CE criteria as train.py builds them also flow through the module's backward
     m.zero_grad()
     logits, _ = m(src, tgt_in, sp, tp, sp.clone(), mask)
@@ -204,5 +207,9 @@ def test_sampled_decode_distribution(oracle):
     f, acc = st.flags(1, "r", False)
     q = O.resample_closed_form(O.masked_probs(lg[0, -1].numpy(), f), acc)
     # a sampled <eos> (id 1) ends the span without being stored: fold it back for the comparison
-    hist = np.bincount(first, minlength=309) / n
-    assert 0.5 * np.abs(hist - q).sum() < 0.08
+    cnt = np.bincount(first, minlength=309).astype(np.float64)
+    assert cnt[q < 1e-30].sum() == 0                         # nothing outside the allowed set
+    big = q * n >= 5
+    chi2 = (((cnt[big] - q[big] * n) ** 2) / (q[big] * n)).sum() + (cnt[~big].sum() - q[~big].sum() * n) ** 2 / max(q[~big].sum() * n, 1e-9)
+    dof = int(big.sum())
+    assert chi2 / dof < 1.35, (chi2, dof)
