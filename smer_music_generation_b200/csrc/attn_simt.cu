@@ -7,7 +7,7 @@
 //
 // Layout: token-major rows.  q[(b*Lq+i)*ldq + h*DH + c], same for k/v/o with their own pitches,
 // so the packed QKV projection output is consumed in place.  lse[(b*H+h)*Lq + i].
-// Dropout element (b,h,i,j) uses Philox counter (((b*H+h)*Lq+i) * ceil(Lk/4) + j/4), lane j%4.
+// Dropout element (b,h,i,j): attn_keep(attn_row_key(seed, site, (b*H+h)*Lq+i), j) -- common.cuh.
 #include "common.cuh"
 #include "../../include/smer_b200.h"
 
@@ -48,12 +48,12 @@ __device__ __forceinline__ float row_dot(const float (&a)[DPT], const float* __r
   return s;
 }
 
-__device__ __forceinline__ void drop_lanes(const AttnParams& p, long long rowid, int lk4, int j4, float (&m)[4]) {
-  uint4 r = philox4x32(p.seed, (uint64_t)(rowid * lk4 + j4), p.site);
-  m[0] = r.x >= p.thr ? p.inv_keep : 0.f;
-  m[1] = r.y >= p.thr ? p.inv_keep : 0.f;
-  m[2] = r.z >= p.thr ? p.inv_keep : 0.f;
-  m[3] = r.w >= p.thr ? p.inv_keep : 0.f;
+__device__ __forceinline__ void drop_lanes(const AttnParams& p, uint32_t rowkey, int j4, float (&m)[4]) {
+  uint32_t b0 = attn_pair_bits(rowkey, j4 * 4), b1 = attn_pair_bits(rowkey, j4 * 4 + 2);
+  m[0] = (b0 & 0xFFFFu) >= p.thr ? p.inv_keep : 0.f;
+  m[1] = (b0 >> 16) >= p.thr ? p.inv_keep : 0.f;
+  m[2] = (b1 & 0xFFFFu) >= p.thr ? p.inv_keep : 0.f;
+  m[3] = (b1 >> 16) >= p.thr ? p.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
-  int lk4 = (p.Lk + 3) >> 2;
+  const uint32_t rowkey = p.thr ? attn_row_key(p.seed, p.site, rowid) : 0u;
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
   const T* vb = (const T*)p.v + (long long)b * p.Lk * p.ldv + h * DH;
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
 #pragma unroll
     for (int j4 = 0; j4 < KT / 4; ++j4) {
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) drop_lanes(p, rowid, lk4, (j0 >> 2) + j4, dm);
+      if (p.thr) drop_lanes(p, rowkey, (j0 >> 2) + j4, dm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int jj = j4 * 4 + u;
@@ -198,9 +198,9 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
   }
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
   float lse = p.lse[rowid], dsum = p.dsum[rowid];
+  const uint32_t rowkey = p.thr ? attn_row_key(p.seed, p.site, rowid) : 0u;
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
-  int lk4 = (p.Lk + 3) >> 2;
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
   const T* vb = (const T*)p.v + (long long)b * p.Lk * p.ldv + h * DH;
   for (int j0 = 0; j0 < kend; j0 += KT) {
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
 #pragma unroll 2
     for (int j4 = 0; j4 < KT / 4; ++j4) {
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) drop_lanes(p, rowid, lk4, (j0 >> 2) + j4, dm);
+      if (p.thr) drop_lanes(p, rowkey, (j0 >> 2) + j4, dm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int jj = j4 * 4 + u;
@@ -279,7 +279,6 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(AttnParams p) {
   }
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   bool key_masked = !row_ok || j >= kend || (p.pad && p.pad[(long long)b * p.Lk + jc]);
-  int lk4 = (p.Lk + 3) >> 2;
   int istart = p.causal ? max(0, (int)(blockIdx.x * ROWS) - p.q_pos0) / KT * KT : 0;     // queries i >= first key of the block
   const T* qb = (const T*)p.q + (long long)b * p.Lq * p.ldq + h * DH;
   const T* gb = (const T*)p.dout + (long long)b * p.Lq * p.lddo + h * DH;
@@ -311,11 +310,8 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(AttnParams p) {
       bool masked = key_masked || (p.causal && j > i + p.q_pos0) || i >= p.Lq;
       float pr = masked ? 0.f : expf(s - Ls[ii]);
       float dmv = 1.f;
-      if (p.thr) {
-        uint4 r = philox4x32(p.seed, (uint64_t)((rowbase + min(i, p.Lq - 1)) * lk4 + (jc >> 2)), p.site);
-        uint32_t rr = (jc & 3) == 0 ? r.x : (jc & 3) == 1 ? r.y : (jc & 3) == 2 ? r.z : r.w;
-        dmv = rr >= p.thr ? p.inv_keep : 0.f;
-      }
+      if (p.thr)
+        dmv = attn_keep(attn_row_key(p.seed, p.site, rowbase + min(i, p.Lq - 1)), jc, p.thr) ? p.inv_keep : 0.f;
       float dp = row_dot<DPT, TPR>(vr, &Gs[ii][part * DPT]) * dmv;
       float ds = pr * (dp - Ds[ii]);
       float pd = pr * dmv;
@@ -353,7 +349,6 @@ template <typename T, int DH>
 __global__ void __launch_bounds__(NTHREADS) attn_weights_kernel(AttnParams p, float* __restrict__ w, long long ldw) {
   int b = blockIdx.z;
   int i = blockIdx.y;
-  int lk4 = (p.Lk + 3) >> 2;
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   for (int j = blockIdx.x * NTHREADS + threadIdx.x; j < p.Lk; j += gridDim.x * NTHREADS) {
     bool masked = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]) || (p.causal && j > i + p.q_pos0);
@@ -368,11 +363,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_weights_kernel(AttnParams p, fl
         if (p.addmask) s += p.addmask[(long long)i * p.ldmask + j];
         long long rowid = ((long long)b * p.H + h) * p.Lq + i;
         float pr = expf(s - p.lse[rowid]);
-        if (p.thr) {
-          uint4 r = philox4x32(p.seed, (uint64_t)(rowid * lk4 + (j >> 2)), p.site);
-          uint32_t rr = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
-          pr = rr >= p.thr ? pr * p.inv_keep : 0.f;
-        }
+        if (p.thr) pr = attn_keep(attn_row_key(p.seed, p.site, rowid), j, p.thr) ? pr * p.inv_keep : 0.f;
         acc += pr;
       }
     }
@@ -394,7 +385,7 @@ static int fill_params(AttnParams& p, const smer_attn_args* a, const char* who) 
   p.addmask = a->add_mask; p.ldmask = a->ld_mask;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale = a->scale; p.causal = a->causal; p.q_pos0 = a->q_pos0;
-  p.thr = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;
+  p.thr = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;      // 16-bit threshold
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site;
   if (p.B <= 0 || p.H <= 0 || p.Lq <= 0 || p.Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }

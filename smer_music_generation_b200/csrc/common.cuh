@@ -133,6 +133,39 @@ __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t site, uint64_t 
   m[3] = r.w >= thr ? inv_keep : 0.f;
 }
 
+// ---------------------------------------------------------------------------------------
+// Attention-probability dropout.  Philox costs ~100 instructions per 4 elements, which would
+// make the softmax warps of the tcgen05 attention kernels the bottleneck several times over;
+// the (B,H,Lq,Lk) keep-mask is instead a counter hash: a 32-bit key per (seed, site, b, h, i)
+// row, then one avalanche mix per PAIR of keys giving two 16-bit uniforms.  The SIMT and
+// tcgen05 kernels (forward, backward, attention-weights) all call these, so they agree bit
+// for bit.  keep(j) = u16 >= thr16, thr16 = round(p * 65536).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+  return x;
+}
+__device__ __forceinline__ uint32_t attn_row_key(uint64_t seed, uint64_t site, long long rowid) {
+  uint32_t a = lowbias32((uint32_t)seed ^ ((uint32_t)site * 0x9E3779B9u) ^ 0x85EBCA6Bu);
+  a = lowbias32(a + (uint32_t)(seed >> 32));
+  a = lowbias32(a ^ (uint32_t)rowid);
+  a = lowbias32(a + (uint32_t)((unsigned long long)rowid >> 32) + 0x632BE5ABu);
+  return a;
+}
+// 32 bits for keys (j & ~1, j | 1): low half for the even key, high half for the odd one
+__device__ __forceinline__ uint32_t attn_pair_bits(uint32_t rowkey, int j) {
+  return lowbias32(rowkey + (uint32_t)(j >> 1) * 0x9E3779B9u);
+}
+__device__ __forceinline__ bool attn_keep(uint32_t rowkey, int j, uint32_t thr16) {
+  return ((attn_pair_bits(rowkey, j) >> ((j & 1) * 16)) & 0xFFFFu) >= thr16;
+}
+static inline uint32_t attn_dropout_thr16(float p) {
+  double t = (double)p * 65536.0 + 0.5;
+  if (t < 0) t = 0;
+  if (t > 65535.0) t = 65535.0;
+  return (uint32_t)t;
+}
+
 static inline uint32_t dropout_threshold(float p) {
   double t = (double)p * 4294967296.0;
   if (t < 0) t = 0;
