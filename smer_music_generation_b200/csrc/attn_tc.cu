@@ -1,12 +1,311 @@
-// tcgen05 flash attention (bf16, dh=64) -- placeholder entry points until the kernels land.
+// Flash-style attention on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16, dh = 64.
+// Arithmetic of F.multi_head_attention_forward's need_weights branch as the reference reaches it
+// (transformer.py:389,459,463): softmax(q k^T / sqrt(dh) + masks) v with dropout on P; masks =
+// causal flag (the nopeek tgt_mask) and per-key padding.  Scores are never materialised in HBM.
+//
+// FORWARD.  CTA = 128 query rows of one (batch, head); KV tiles of 128 keys.
+//   warp 0      TMA producer: Q once, then K_t / V_t into single smem slots (K's slot is free as
+//               soon as S_t = Q K_t^T has been read by the tensor core, V's after O_t = P_t V_t)
+//   warp 1      tcgen05.mma issuer (one elected thread) + TMEM owner (256 columns: S 128, O_t 64)
+//   warps 2..5  softmax: thread <-> TMEM lane <-> query row.  Two passes over S in TMEM (max, then
+//               exp2 / row-sum / dropout / bf16 pack), P written to smem in the SWIZZLE_128B
+//               K-major layout the PV MMA reads; O accumulated in fp32 registers with the
+//               online-softmax rescale after each PV tile.
+//   Two CTAs share an SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
+//   other's MMAs.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/smer_b200.h"
 
-extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
-  (void)a; (void)stream;
-  smer_set_error("smer_attn_fwd_tc: not implemented in this build");
-  return SMER_ERR_UNSUPPORTED;
+int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
+                        int box_inner, int box_outer);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, DH = 64;
+constexpr int TILE_QKV = BM * DH * 2;            // 16 KB
+constexpr int TILE_P = BM * BN * 2;              // 32 KB (two 64-key halves of 16 KB)
+constexpr int FWD_THREADS = 192;
+constexpr int FWD_SMEM = 3 * TILE_QKV + TILE_P + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;
+constexpr int O_COL = 128;
+
+struct FwdParams {
+  bf16* o;
+  long long ldo;
+  float* lse;
+  const int* kv_len;
+  const uint8_t* pad;
+  int B, H, Lq, Lk;
+  float c_log2;            // scale * log2(e)
+  int causal;
+  uint32_t thr16;
+  float inv_keep;
+  uint64_t seed, site;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_QKV;
+  uint8_t* sV = smem + 2 * TILE_QKV;
+  uint8_t* sP = smem + 3 * TILE_QKV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_QKV + TILE_P);
+  uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *k_empty = bars + 3, *v_empty = bars + 4,
+           *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* padw = tmem_ptr + 2;                 // [2][4] mask words of the current KV tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;     // heavy (late-causal) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int i0 = qt * BM;
+  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  if (p.causal) kend = min(kend, i0 + BM);
+  const int ntiles = (kend + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 128 : 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      if (ntiles > 0) {
+        ptx::mbar_expect_tx(q_full, TILE_QKV);
+        ptx::tma_load_2d(sQ, &tmQ, q_full, h * DH, b * p.Lq + i0);
+      }
+      for (int t = 0; t < ntiles; ++t) {
+        if (t > 0) ptx::mbar_wait(k_empty, (t - 1) & 1);
+        ptx::mbar_expect_tx(k_full, TILE_QKV);
+        ptx::tma_load_2d(sK, &tmK, k_full, h * DH, b * p.Lk + t * BN);
+        if (t > 0) ptx::mbar_wait(v_empty, (t - 1) & 1);
+        ptx::mbar_expect_tx(v_full, TILE_QKV);
+        ptx::tma_load_2d(sV, &tmV, v_full, h * DH, b * p.Lk + t * BN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
+      const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aP = ptx::smem_u32(sP);
+      if (ntiles > 0) ptx::mbar_wait(q_full, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        ptx::mbar_wait(k_full, t & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_bf16_ss(tmem_base, ptx::make_smem_desc(aQ + k * 32, 16, 1024), ptx::make_smem_desc(aK + k * 32, 16, 1024),
+                            idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(k_empty);
+        ptx::umma_commit(s_full);
+        ptx::mbar_wait(p_full, t & 1);
+        ptx::mbar_wait(v_full, t & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint32_t pa = aP + (k >> 2) * (TILE_P / 2) + (k & 3) * 32;       // K-major, two 64-key halves
+          ptx::umma_bf16_ss(tmem_base + O_COL, ptx::make_smem_desc(pa, 16, 1024),
+                            ptx::make_smem_desc(aV + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(v_empty);
+        ptx::umma_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int i = i0 + r;
+    const bool row_ok = i < p.Lq;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sP_row = ptx::smem_u32(sP) + r * 128;
+    const uint32_t rx = (uint32_t)(r & 7);
+    const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
+    const uint32_t rowkey = p.thr16 ? attn_row_key(p.seed, p.site, rowid) : 0u;
+    const float c2 = p.c_log2;
+    float m = -INFINITY, l = 0.f;
+    float acc[DH];
+#pragma unroll
+    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = t * BN;
+      uint32_t mw[4] = {0u, 0u, 0u, 0u};
+      if (p.pad != nullptr || j0 + BN > kend) {
+        const int j = j0 + r;
+        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
+        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
+        if (lane == 0) padw[(t & 1) * 4 + quarter] = bal;
+        bar_sync_softmax();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mw[c] = padw[(t & 1) * 4 + c];
+      }
+      if (p.causal && j0 + BN - 1 > i0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int nvis = i - (j0 + c * 32) + 1;
+          mw[c] |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
+        }
+      }
+      ptx::mbar_wait(s_full, t & 1);
+      ptx::tc_fence_after();
+      // ---- pass 1: row maximum of the visible scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(lane_addr + c * 32, v);
+        ptx::tmem_ld_wait();
+        const uint32_t w = mw[c];
+        if (w == 0u) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, ((w >> k) & 1u) ? -INFINITY : __uint_as_float(v[k]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * c2);
+      const float m_use = m_new == -INFINITY ? 0.f : m_new;
+      const float alpha = ex2(m - m_use);
+      float lsum = 0.f;
+      // ---- pass 2: P = exp2(S*c - m), row sum, dropout, bf16 pack into the swizzled A-operand tile
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(lane_addr + c * 32, v);
+        ptx::tmem_ld_wait();
+        const uint32_t w = mw[c];
+        float pv[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float s = __uint_as_float(v[k]);
+          if (w != 0u) s = ((w >> k) & 1u) ? -INFINITY : s;
+          pv[k] = ex2(fmaf(s, c2, -m_use));
+          lsum += pv[k];
+        }
+        if (p.thr16) {
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            const uint32_t bits = attn_pair_bits(rowkey, j0 + c * 32 + 2 * k2);
+            pv[2 * k2] = (bits & 0xFFFFu) >= p.thr16 ? pv[2 * k2] * p.inv_keep : 0.f;
+            pv[2 * k2 + 1] = (bits >> 16) >= p.thr16 ? pv[2 * k2 + 1] * p.inv_keep : 0.f;
+          }
+        }
+        const uint32_t half_base = sP_row + (c >> 1) * (TILE_P / 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t c16 = (uint32_t)((c & 1) * 4 + q);
+          st_shared_v4(half_base + ((c16 ^ rx) << 4), pack_bf16x2(pv[8 * q], pv[8 * q + 1]),
+                       pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]), pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]),
+                       pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
+        }
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core
+      ptx::tc_fence_before();            // orders this thread's tcgen05.ld before the next MMAs
+      ptx::mbar_arrive(p_full);
+      // ---- O += P V  (rescale the running accumulator, add the tile result)
+      ptx::mbar_wait(o_full, t & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(lane_addr + O_COL + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[c * 32 + k] = fmaf(acc[c * 32 + k], alpha, __uint_as_float(v[k]));
+      }
+    }
+    if (row_ok) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH;
+#pragma unroll
+      for (int c = 0; c < DH; c += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(acc[c] * inv, acc[c + 1] * inv);
+        u.y = pack_bf16x2(acc[c + 2] * inv, acc[c + 3] * inv);
+        u.z = pack_bf16x2(acc[c + 4] * inv, acc[c + 5] * inv);
+        u.w = pack_bf16x2(acc[c + 6] * inv, acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + c) = u;
+      }
+      if (p.lse) p.lse[((long long)b * p.H + h) * p.Lq + i] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+int check_common(const smer_attn_args* a, const char* who) {
+  if (!a) { smer_set_error("%s: null args", who); return SMER_ERR_ARG; }
+  if (a->dtype != SMER_DT_BF16 || a->dh != DH) {
+    smer_set_error("%s: bf16 with head dim 64 only (dtype=%d dh=%d)", who, a->dtype, a->dh);
+    return SMER_ERR_UNSUPPORTED;
+  }
+  if (a->add_mask || a->q_pos0 != 0) {
+    smer_set_error("%s: additive masks / query offsets are served by the simt kernels", who);
+    return SMER_ERR_UNSUPPORTED;
+  }
+  if (a->causal && a->Lq != a->Lk) { smer_set_error("%s: causal needs Lq == Lk", who); return SMER_ERR_UNSUPPORTED; }
+  if (a->B <= 0 || a->H <= 0 || a->Lq <= 0 || a->Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }
+  return SMER_OK;
+}
+
+}  // namespace
+
+extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
+  int rc = check_common(a, "smer_attn_fwd_tc");
+  if (rc) return rc;
+  SMER_CHECK_ARG(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "smer_attn_fwd_tc: o must be 16-byte aligned rows");
+  CUtensorMap tq, tk, tv;
+  const long long dcols = (long long)a->H * DH;
+  if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, (long long)a->B * a->Lq, a->ldq, DH, BM))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, (long long)a->B * a->Lk, a->ldk, DH, BN))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, (long long)a->B * a->Lk, a->ldv, DH, BN))) return rc;
+  FwdParams p;
+  p.o = (bf16*)a->o; p.ldo = a->ldo; p.lse = a->lse; p.kv_len = a->kv_len; p.pad = a->key_pad;
+  p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
+  p.c_log2 = a->scale * 1.4426950408889634f;
+  p.causal = a->causal;
+  p.thr16 = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;
+  p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
+  p.seed = a->seed; p.site = a->site;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMER_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((a->Lq + BM - 1) / BM, a->H, a->B);
+  attn_fwd_tc_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  SMER_CHECK_LAUNCH("smer_attn_fwd_tc");
+  return SMER_OK;
+}
+
 extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   (void)a; (void)stream;
   smer_set_error("smer_attn_bwd_tc: not implemented in this build");
