@@ -275,6 +275,48 @@ def test_attention_fwd_bwd(dev, dtype, H, dh, Lq, Lk, causal, use_pad):
     assert rel(dkv[:, d:].reshape(B, Lk, d), vr.grad) < btol
 
 
+@pytest.mark.parametrize("Lq,Lk,causal,use_pad,drop", [(128, 128, False, False, 0.0), (256, 256, True, False, 0.0),
+                                                       (200, 200, True, True, 0.0), (1024, 1024, True, True, 0.0),
+                                                       (100, 777, False, True, 0.0), (384, 1024, False, True, 0.1),
+                                                       (512, 512, True, True, 0.1), (1, 130, False, False, 0.0)])
+def test_attention_tc_fwd_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
+    """tcgen05 forward == CUDA-core forward on the same bf16 inputs (same dropout mask: both use
+    the counter hash of common.cuh) and == torch fp32 when dropout is off."""
+    ops, K = _ops()
+    assert ops.ATTN_TC_FWD
+    g = torch.Generator().manual_seed(Lq * 3 + Lk)
+    B, H, dh = 2, 8, 64
+    d = H * dh
+    qkv = torch.randn(B * Lq, 3 * d, generator=g).to(dev).bfloat16()
+    kvb = torch.randn(B * Lk, 2 * d, generator=g).to(dev).bfloat16()
+    q, k, v = qkv[:, :d], kvb[:, :d], kvb[:, d:]
+    pad = kv_len = None
+    if use_pad:
+        lens = torch.tensor([Lk, max(1, Lk - 37)])
+        pad = (torch.arange(Lk)[None] >= lens[:, None]).to(torch.uint8).to(dev)
+        if not causal:
+            pad[1, Lk // 3] = 1                  # a non-suffix masked key: honoured through the per-key mask
+        kv_len = lens.to(torch.int32).to(dev)
+    outs = {}
+    for path in ("tc", "simt"):
+        ops._TC_ATTN = path
+        o = torch.full((B * Lq, d), float("nan"), dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(B, H, Lq, device=dev)
+        a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=pad, kv_len=kv_len,
+                          dropout_p=drop, seed=77, site=3)
+        ops.attn_fwd(a)
+        torch.cuda.synchronize()
+        outs[path] = (o, lse)
+    ops._TC_ATTN = "tc"
+    assert torch.isfinite(outs["tc"][0].float()).all()
+    assert rel(outs["tc"][0], outs["simt"][0]) < 2e-2
+    assert (outs["tc"][1] - outs["simt"][1]).abs().max().item() < 2e-3
+    if drop == 0.0:
+        ref, _ = _ref_attn(q.float().reshape(B, Lq, d), k.float().reshape(B, Lk, d), v.float().reshape(B, Lk, d), H,
+                           causal, pad)
+        assert rel(outs["tc"][0].view(B, Lq, d), ref) < 2e-2
+
+
 def test_attention_qpos_and_addmask(dev):
     ops, K = _ops()
     g = torch.Generator().manual_seed(9)

@@ -38,7 +38,7 @@ def test_state_dict_layout_matches_reference(golden_dir):
         assert torch.equal(mine[k].cpu(), v), k
 
 
-@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 1e-3), ("bf16", 2e-2, 1.5e-1)])
+@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 1e-3), ("bf16", 2e-2, 2.5e-1)])
 def test_forward_loss_grads_vs_reference(golden_dir, mode, tol, gtol):
     from smer_music_generation_b200 import SmerLoss
     g = _load(golden_dir, "fwd_small.pt")
