@@ -261,6 +261,437 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+
+// =========================================================================================
+// BACKWARD.  Two kernels, both with the forward's warp roles (TMA producer / MMA issuer /
+// 128 softmax threads, thread <-> TMEM lane) and two CTAs per SM:
+//   dQ kernel  : CTA = 128 query rows, loop over 64-key tiles.  S = Q K^T and dP = dO V^T into
+//                TMEM; threads form dS = P o (dP*keep/(1-p) - D) in bf16 (smem, A operand);
+//                dQ += dS K accumulates in TMEM over the whole loop (no rescale in backward).
+//   dKV kernel : CTA = 128 keys, loop over 64-query tiles.  S^T = K Q^T, dP^T = V dO^T; threads
+//                (<-> key row) write P^T*keep and dS^T; dV += P^T dO, dK += dS^T Q in TMEM.
+// P is recomputed from the saved log-sum-exp; D = rowsum(dO o O) comes from a small pre-kernel.
+// =========================================================================================
+constexpr int BKV = 64;                         // second tile dimension of both backward kernels
+constexpr int TILE_HALF = BKV * DH * 2;         // 8 KB
+constexpr int BWD_THREADS = 192;
+constexpr int DQ_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + TILE_QKV + 1024 + 256;
+constexpr int DKV_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + 2 * TILE_QKV + 1024 + 2048;
+
+struct BwdParams {
+  bf16 *dq, *dk, *dv;
+  long long lddq, lddk, lddv;
+  const float* lse;
+  const float* dsum;
+  const int* kv_len;
+  const uint8_t* pad;
+  int B, H, Lq, Lk;
+  float c_log2, scale;
+  int causal;
+  uint32_t thr16;
+  float inv_keep;
+  uint64_t seed, site;
+};
+
+// 8 consecutive bf16 of row `r` (16-byte chunk c16 of a 128-byte SWIZZLE_128B row)
+__device__ __forceinline__ void st_row_chunk(uint32_t row_addr, uint32_t rx, uint32_t c16, const float* v) {
+  st_shared_v4(row_addr + ((c16 ^ rx) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+               pack_bf16x2(v[6], v[7]));
+}
+
+template <typename T>
+__global__ void attn_dsum_kernel(const T* __restrict__ o, long long ldo, const T* __restrict__ g, long long ldg,
+                                 float* __restrict__ dsum, int B, int H, int Lq) {
+  // 8 lanes per (row, head): 16-byte loads, shuffle reduction
+  long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
+  int part = threadIdx.x & 7;
+  long long n = (long long)B * Lq * H;
+  if (t >= n) return;
+  int h = (int)(t % H);
+  long long row = t / H;                         // b*Lq + i
+  uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + h * DH + part * 8);
+  uint4 c = *reinterpret_cast<const uint4*>(g + row * ldg + h * DH + part * 8);
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 x = __bfloat1622float2(pa[k]), y = __bfloat1622float2(pc[k]);
+    s = fmaf(x.x, y.x, s);
+    s = fmaf(x.y, y.y, s);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (part == 0) {
+    int b = (int)(row / Lq), i = (int)(row % Lq);
+    dsum[((long long)b * H + h) * Lq + i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + TILE_QKV;
+  uint8_t* sK = smem + 2 * TILE_QKV;                 // [2] x 8 KB
+  uint8_t* sV = sK + 2 * TILE_HALF;                  // [2] x 8 KB
+  uint8_t* sdS = sV + 2 * TILE_HALF;                 // 16 KB: [128 q][64 keys] K-major
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_QKV);
+  uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_empty = bars + 3 /*[2]*/, *sp_full = bars + 5,
+           *ds_full = bars + 6, *dq_done = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* padw = tmem_ptr + 2;                     // [2][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int i0 = qt * BM;
+  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  if (p.causal) kend = min(kend, i0 + BM);
+  const int ntiles = (kend + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 128 : 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (ptx::elect_one() && ntiles > 0) {
+      ptx::mbar_expect_tx(qdo_full, 2 * TILE_QKV);
+      ptx::tma_load_2d(sQ, &tmQ, qdo_full, h * DH, b * p.Lq + i0);
+      ptx::tma_load_2d(sdO, &tmdO, qdo_full, h * DH, b * p.Lq + i0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        if (t >= 2) ptx::mbar_wait(kv_empty + s, ((t - 2) >> 1) & 1);
+        ptx::mbar_expect_tx(kv_full + s, 2 * TILE_HALF);
+        ptx::tma_load_2d(sK + s * TILE_HALF, &tmK, kv_full + s, h * DH, b * p.Lk + t * BKV);
+        ptx::tma_load_2d(sV + s * TILE_HALF, &tmV, kv_full + s, h * DH, b * p.Lk + t * BKV);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (ptx::elect_one() && ntiles > 0) {
+      constexpr uint32_t idesc_kk = ptx::make_idesc_bf16(BM, BKV, 0, 0);     // both operands K-major
+      constexpr uint32_t idesc_kn = ptx::make_idesc_bf16(BM, DH, 0, 1);      // B MN-major
+      const uint32_t aQ = ptx::smem_u32(sQ), adO = ptx::smem_u32(sdO), adS = ptx::smem_u32(sdS);
+      ptx::mbar_wait(qdo_full, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        const uint32_t aK = ptx::smem_u32(sK + s * TILE_HALF), aV = ptx::smem_u32(sV + s * TILE_HALF);
+        ptx::mbar_wait(kv_full + s, (t >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_bf16_ss(tmem_base, ptx::make_smem_desc(aQ + k * 32, 16, 1024), ptx::make_smem_desc(aK + k * 32, 16, 1024),
+                            idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          ptx::umma_bf16_ss(tmem_base + 64, ptx::make_smem_desc(adO + k * 32, 16, 1024),
+                            ptx::make_smem_desc(aV + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+        ptx::umma_commit(sp_full);
+        ptx::mbar_wait(ds_full, t & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          ptx::umma_bf16_ss(tmem_base + 128, ptx::make_smem_desc(adS + k * 32, 16, 1024),
+                            ptx::make_smem_desc(aK + k * 2048, 8192, 1024), idesc_kn, (t > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit(kv_empty + s);
+      }
+      ptx::umma_commit(dq_done);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int i = i0 + r;
+    const bool row_ok = i < p.Lq;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t row_addr = ptx::smem_u32(sdS) + r * 128;
+    const uint32_t rx = (uint32_t)(r & 7);
+    const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
+    const uint32_t rowkey = p.thr16 ? attn_row_key(p.seed, p.site, rowid) : 0u;
+    float lse2 = INFINITY, dsum = 0.f;
+    if (row_ok) {
+      const float l = p.lse[rowid];
+      lse2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
+      dsum = p.dsum[rowid];
+    }
+    const float c2 = p.c_log2;
+    for (int t = 0; t < ntiles; ++t) {
+      const int j0 = t * BKV;
+      uint32_t mw[2] = {0u, 0u};
+      if (p.pad != nullptr || j0 + BKV > kend) {
+        const int j = j0 + (r & 63);
+        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
+        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
+        if (lane == 0) padw[(t & 1) * 2 + (quarter & 1)] = bal;       // quarters 0/2 and 1/3 write equal words
+        bar_sync_softmax();
+        mw[0] = padw[(t & 1) * 2];
+        mw[1] = padw[(t & 1) * 2 + 1];
+      }
+      if (p.causal && j0 + BKV - 1 > i0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int nvis = i - (j0 + c * 32) + 1;
+          mw[c] |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
+        }
+      }
+      ptx::mbar_wait(sp_full, t & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        ptx::tmem_ld_32x32(lane_addr + c * 32, sv);
+        ptx::tmem_ld_32x32(lane_addr + 64 + c * 32, dv);
+        ptx::tmem_ld_wait();
+        const uint32_t w = mw[c];
+        float ds[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lse2));
+          if (w != 0u) pr = ((w >> k) & 1u) ? 0.f : pr;
+          float dp = __uint_as_float(dv[k]);
+          if (p.thr16) {
+            const uint32_t bits = attn_pair_bits(rowkey, j0 + c * 32 + k);
+            dp = ((bits >> ((k & 1) * 16)) & 0xFFFFu) >= p.thr16 ? dp * p.inv_keep : 0.f;
+          }
+          ds[k] = pr * (dp - dsum);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st_row_chunk(row_addr, rx, (uint32_t)(c * 4 + q), ds + 8 * q);
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(ds_full);
+    }
+    if (ntiles > 0) {
+      ptx::mbar_wait(dq_done, 0);
+      ptx::tc_fence_after();
+    }
+    bf16* drow = p.dq + ((long long)b * p.Lq + i) * p.lddq + h * DH;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      if (ntiles > 0) {                    // warp-uniform: tcgen05.ld is .sync.aligned
+        ptx::tmem_ld_32x32(lane_addr + 128 + c * 32, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0u;
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[k]) * p.scale, __uint_as_float(v[k + 1]) * p.scale);
+          u.y = pack_bf16x2(__uint_as_float(v[k + 2]) * p.scale, __uint_as_float(v[k + 3]) * p.scale);
+          u.z = pack_bf16x2(__uint_as_float(v[k + 4]) * p.scale, __uint_as_float(v[k + 5]) * p.scale);
+          u.w = pack_bf16x2(__uint_as_float(v[k + 6]) * p.scale, __uint_as_float(v[k + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(drow + c * 32 + k) = u;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_QKV;
+  uint8_t* sQ = smem + 2 * TILE_QKV;                 // [2] x 8 KB  (64 query rows each)
+  uint8_t* sdO = sQ + 2 * TILE_HALF;                 // [2] x 8 KB
+  uint8_t* sPd = sdO + 2 * TILE_HALF;                // 16 KB: [128 keys][64 q] K-major, P^T * keep/(1-p)
+  uint8_t* sdS = sPd + TILE_QKV;                     // 16 KB: [128 keys][64 q] K-major, dS^T
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_QKV);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *sp_full = bars + 5,
+           *pds_full = bars + 6, *done = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_lse = reinterpret_cast<float*>(tmem_ptr + 2);      // [2][64]
+  float* s_dsum = s_lse + 2 * BKV;                            // [2][64]
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_dsum + 2 * BKV);   // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int j0 = blockIdx.x * BM;
+  const int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  const int nq = (p.Lq + BKV - 1) / BKV;
+  const int it0 = p.causal ? j0 / BKV : 0;           // queries i >= j0 only
+  const int ntiles = j0 < kend ? max(0, nq - it0) : 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 128 : 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (ptx::elect_one() && ntiles > 0) {
+      ptx::mbar_expect_tx(kv_full, 2 * TILE_QKV);
+      ptx::tma_load_2d(sK, &tmK, kv_full, h * DH, b * p.Lk + j0);
+      ptx::tma_load_2d(sV, &tmV, kv_full, h * DH, b * p.Lk + j0);
+      for (int n = 0; n < ntiles; ++n) {
+        const int s = n & 1;
+        if (n >= 2) ptx::mbar_wait(qdo_empty + s, ((n - 2) >> 1) & 1);
+        ptx::mbar_expect_tx(qdo_full + s, 2 * TILE_HALF);
+        ptx::tma_load_2d(sQ + s * TILE_HALF, &tmQ, qdo_full + s, h * DH, b * p.Lq + (it0 + n) * BKV);
+        ptx::tma_load_2d(sdO + s * TILE_HALF, &tmdO, qdo_full + s, h * DH, b * p.Lq + (it0 + n) * BKV);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (ptx::elect_one() && ntiles > 0) {
+      constexpr uint32_t idesc_kk = ptx::make_idesc_bf16(BM, BKV, 0, 0);
+      constexpr uint32_t idesc_kn = ptx::make_idesc_bf16(BM, DH, 0, 1);
+      const uint32_t aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aPd = ptx::smem_u32(sPd), adS = ptx::smem_u32(sdS);
+      ptx::mbar_wait(kv_full, 0);
+      for (int n = 0; n < ntiles; ++n) {
+        const int s = n & 1;
+        const uint32_t aQ = ptx::smem_u32(sQ + s * TILE_HALF), adO = ptx::smem_u32(sdO + s * TILE_HALF);
+        ptx::mbar_wait(qdo_full + s, (n >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)          // S^T = K Q^T
+          ptx::umma_bf16_ss(tmem_base, ptx::make_smem_desc(aK + k * 32, 16, 1024), ptx::make_smem_desc(aQ + k * 32, 16, 1024),
+                            idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)          // dP^T = V dO^T
+          ptx::umma_bf16_ss(tmem_base + 64, ptx::make_smem_desc(aV + k * 32, 16, 1024),
+                            ptx::make_smem_desc(adO + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+        ptx::umma_commit(sp_full);
+        ptx::mbar_wait(pds_full, n & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)         // dV += (P^T keep) dO
+          ptx::umma_bf16_ss(tmem_base + 192, ptx::make_smem_desc(aPd + k * 32, 16, 1024),
+                            ptx::make_smem_desc(adO + k * 2048, 8192, 1024), idesc_kn, (n > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)         // dK += dS^T Q
+          ptx::umma_bf16_ss(tmem_base + 128, ptx::make_smem_desc(adS + k * 32, 16, 1024),
+                            ptx::make_smem_desc(aQ + k * 2048, 8192, 1024), idesc_kn, (n > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit(qdo_empty + s);
+      }
+      ptx::umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int j = j0 + r;
+    const bool row_ok = j < p.Lk;
+    const bool key_masked = j >= kend || (p.pad && row_ok && p.pad[(long long)b * p.Lk + j]);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t pd_row = ptx::smem_u32(sPd) + r * 128;
+    const uint32_t ds_row = ptx::smem_u32(sdS) + r * 128;
+    const uint32_t rx = (uint32_t)(r & 7);
+    const uint32_t jsh = (uint32_t)((j & 1) * 16);
+    const long long rowbase = ((long long)b * p.H + h) * p.Lq;
+    const float c2 = p.c_log2;
+    for (int n = 0; n < ntiles; ++n) {
+      const int iq0 = (it0 + n) * BKV;
+      const int slot = (n & 1) * BKV;
+      if (r < BKV) {
+        const int i = iq0 + r;
+        float l2 = INFINITY, ds_ = 0.f;
+        uint32_t rk = 0u;
+        if (i < p.Lq) {
+          const float l = p.lse[rowbase + i];
+          l2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
+          ds_ = p.dsum[rowbase + i];
+          if (p.thr16) rk = attn_row_key(p.seed, p.site, rowbase + i);
+        }
+        s_lse[slot + r] = l2;
+        s_dsum[slot + r] = ds_;
+        s_key[slot + r] = rk;
+      }
+      bar_sync_softmax();
+      const int cm = (p.causal && iq0 < j0 + BM) ? (j - iq0) : 0;       // query columns < cm cannot see key j
+      ptx::mbar_wait(sp_full, n & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        ptx::tmem_ld_32x32(lane_addr + c * 32, sv);
+        ptx::tmem_ld_32x32(lane_addr + 64 + c * 32, dv);
+        ptx::tmem_ld_wait();
+        float pd[32], ds[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int col = c * 32 + k;
+          float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -s_lse[slot + col]));
+          if (key_masked || col < cm) pr = 0.f;
+          float keep = 1.f;
+          if (p.thr16) keep = ((attn_pair_bits(s_key[slot + col], j) >> jsh) & 0xFFFFu) >= p.thr16 ? p.inv_keep : 0.f;
+          pd[k] = pr * keep;
+          ds[k] = pr * (__uint_as_float(dv[k]) * keep - s_dsum[slot + col]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          st_row_chunk(pd_row, rx, (uint32_t)(c * 4 + q), pd + 8 * q);
+          st_row_chunk(ds_row, rx, (uint32_t)(c * 4 + q), ds + 8 * q);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(pds_full);
+    }
+    if (ntiles > 0) {
+      ptx::mbar_wait(done, 0);
+      ptx::tc_fence_after();
+    }
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {           // 0: dK (scaled), 1: dV
+      bf16* drow = (part == 0 ? p.dk + ((long long)b * p.Lk + j) * p.lddk : p.dv + ((long long)b * p.Lk + j) * p.lddv) + h * DH;
+      const float sc = part == 0 ? p.scale : 1.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        if (ntiles > 0) {
+          ptx::tmem_ld_32x32(lane_addr + 128 + part * 64 + c * 32, v);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0u;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[k]) * sc, __uint_as_float(v[k + 1]) * sc);
+            u.y = pack_bf16x2(__uint_as_float(v[k + 2]) * sc, __uint_as_float(v[k + 3]) * sc);
+            u.z = pack_bf16x2(__uint_as_float(v[k + 4]) * sc, __uint_as_float(v[k + 5]) * sc);
+            u.w = pack_bf16x2(__uint_as_float(v[k + 6]) * sc, __uint_as_float(v[k + 7]) * sc);
+            *reinterpret_cast<uint4*>(drow + c * 32 + k) = u;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
 int check_common(const smer_attn_args* a, const char* who) {
   if (!a) { smer_set_error("%s: null args", who); return SMER_ERR_ARG; }
   if (a->dtype != SMER_DT_BF16 || a->dh != DH) {
@@ -307,7 +738,49 @@ extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
 }
 
 extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
-  (void)a; (void)stream;
-  smer_set_error("smer_attn_bwd_tc: not implemented in this build");
-  return SMER_ERR_UNSUPPORTED;
+  int rc = check_common(a, "smer_attn_bwd_tc");
+  if (rc) return rc;
+  SMER_CHECK_ARG(a->dout && a->dq && a->dk && a->dv && a->lse && a->dsum && a->o, "smer_attn_bwd_tc: missing buffers");
+  SMER_CHECK_ARG(a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0 && a->ldo % 8 == 0 && a->lddo % 8 == 0,
+                 "smer_attn_bwd_tc: row pitches must be multiples of 8 elements");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long dcols = (long long)a->H * DH;
+  const long long rq = (long long)a->B * a->Lq, rk = (long long)a->B * a->Lk;
+  {
+    long long n = rq * a->H * 8;
+    attn_dsum_kernel<bf16><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, a->ldo, (const bf16*)a->dout, a->lddo,
+                                                                         a->dsum, a->B, a->H, a->Lq);
+  }
+  BwdParams p;
+  p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv;
+  p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.lse = a->lse; p.dsum = a->dsum; p.kv_len = a->kv_len; p.pad = a->key_pad;
+  p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
+  p.c_log2 = a->scale * 1.4426950408889634f; p.scale = a->scale; p.causal = a->causal;
+  p.thr16 = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;
+  p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
+  p.seed = a->seed; p.site = a->site;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMER_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    SMER_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    attr_set = true;
+  }
+  CUtensorMap tq, tdo, tk, tv;
+  // dQ kernel: 128-row Q / dO boxes, 64-row K / V boxes
+  if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, rq, a->ldq, DH, BM))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tdo, a->dout, dcols, rq, a->lddo, DH, BM))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, rk, a->ldk, DH, BKV))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, rk, a->ldv, DH, BKV))) return rc;
+  dim3 gq((a->Lq + BM - 1) / BM, a->H, a->B);
+  attn_bwd_dq_tc_kernel<<<gq, BWD_THREADS, DQ_SMEM, st>>>(tq, tdo, tk, tv, p);
+  // dKV kernel: 64-row Q / dO boxes, 128-row K / V boxes
+  if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, rq, a->ldq, DH, BKV))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tdo, a->dout, dcols, rq, a->lddo, DH, BKV))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, rk, a->ldk, DH, BM))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, rk, a->ldv, DH, BM))) return rc;
+  dim3 gk((a->Lk + BM - 1) / BM, a->H, a->B);
+  attn_bwd_dkv_tc_kernel<<<gk, BWD_THREADS, DKV_SMEM, st>>>(tq, tdo, tk, tv, p);
+  SMER_CHECK_LAUNCH("smer_attn_bwd_tc");
+  return SMER_OK;
 }

@@ -204,7 +204,7 @@ def attn_weights(a, w):
 # Which tcgen05 attention kernels this build provides (attn_tc.cu); the dispatcher above is a
 # capability table of the one library, not a backend switch.
 ATTN_TC_FWD = True
-ATTN_TC_BWD = False
+ATTN_TC_BWD = True
 
 
 def xent_fwd(logits, targets, W, Cw, category, ncat, lse, sums, V):

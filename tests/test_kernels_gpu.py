@@ -279,7 +279,7 @@ def test_attention_fwd_bwd(dev, dtype, H, dh, Lq, Lk, causal, use_pad):
                                                        (200, 200, True, True, 0.0), (1024, 1024, True, True, 0.0),
                                                        (100, 777, False, True, 0.0), (384, 1024, False, True, 0.1),
                                                        (512, 512, True, True, 0.1), (1, 130, False, False, 0.0)])
-def test_attention_tc_fwd_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
+def test_attention_tc_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
     """tcgen05 forward == CUDA-core forward on the same bf16 inputs (same dropout mask: both use
     the counter hash of common.cuh) and == torch fp32 when dropout is off."""
     ops, K = _ops()
@@ -315,6 +315,34 @@ def test_attention_tc_fwd_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
         ref, _ = _ref_attn(q.float().reshape(B, Lq, d), k.float().reshape(B, Lk, d), v.float().reshape(B, Lk, d), H,
                            causal, pad)
         assert rel(outs["tc"][0].view(B, Lq, d), ref) < 2e-2
+    # ---- backward: tcgen05 kernels vs CUDA-core kernels from the same forward state
+    assert ops.ATTN_TC_BWD
+    o, lse = outs["simt"]
+    do = torch.randn(B * Lq, d, generator=g).to(dev).bfloat16()
+    grads = {}
+    for path in ("tc", "simt"):
+        ops._TC_ATTN = path
+        dqkv = torch.full((B * Lq, 3 * d), float("nan"), dtype=torch.bfloat16, device=dev)
+        dkv = torch.full((B * Lk, 2 * d), float("nan"), dtype=torch.bfloat16, device=dev)
+        dsum = torch.empty(B, H, Lq, device=dev)
+        a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=pad, kv_len=kv_len,
+                          dropout_p=drop, seed=77, site=3, dout=do, dq=dqkv[:, :d], dk=dkv[:, :d], dv=dkv[:, d:], dsum=dsum)
+        ops.attn_bwd(a)
+        torch.cuda.synchronize()
+        grads[path] = (dqkv[:, :d].clone(), dkv[:, :d].clone(), dkv[:, d:].clone())
+    ops._TC_ATTN = "tc"
+    for name, x, y in zip(("dq", "dk", "dv"), grads["tc"], grads["simt"]):
+        assert torch.isfinite(x.float()).all(), name
+        assert rel(x, y) < 3e-2, (name, rel(x, y))
+    if drop == 0.0:
+        qr = q.float().reshape(B, Lq, d).requires_grad_(True)
+        kr = k.float().reshape(B, Lk, d).requires_grad_(True)
+        vr = v.float().reshape(B, Lk, d).requires_grad_(True)
+        ref, _ = _ref_attn(qr, kr, vr, H, causal, pad)
+        ref.backward(do.float().view(B, Lq, d))
+        assert rel(grads["tc"][0].view(B, Lq, d), qr.grad) < 3e-2
+        assert rel(grads["tc"][1].view(B, Lk, d), kr.grad) < 3e-2
+        assert rel(grads["tc"][2].view(B, Lk, d), vr.grad) < 3e-2
 
 
 def test_attention_qpos_and_addmask(dev):
