@@ -592,6 +592,8 @@ class _Run:
         if hook:
             hook("fc.")
         dy, _ = self._ln_bwd(dyo, self.dec_norm, 0, "dec.norm", grads, "transformer.decoder.norm.", has_resid=False)
+        if hook:
+            hook("transformer.decoder.norm.")
         mem = self.tape.pop("mem")
         dmem = torch.zeros(B * S, d, dtype=self.dt, device=self.dev)
         for i in reversed(range(len(self.dec_p))):
@@ -609,9 +611,9 @@ class _Run:
                 hook(n)
         emb_scale = math.sqrt(d)
         ops.embed_bwd(self.tgt, dy, grads["embedding.weight"], emb_scale, self.pd, self.seed, _SITE_EMB_TGT)
-        if hook:
-            hook("transformer.decoder.norm.")
         dx, _ = self._ln_bwd(dmem, self.enc_norm, 0, "enc.norm", grads, "transformer.encoder.norm.", has_resid=False)
+        if hook:
+            hook("transformer.encoder.norm.")
         for i in reversed(range(len(self.enc_p))):
             lp = self.enc_p[i]
             n = lp.name
@@ -624,7 +626,6 @@ class _Run:
                 hook(n)
         ops.embed_bwd(self.src, dx, grads["embedding.weight"], emb_scale, self.pd, self.seed, _SITE_EMB_SRC)
         if hook:
-            hook("transformer.encoder.norm.")
             hook("embedding.")
         self.tape.clear()
 

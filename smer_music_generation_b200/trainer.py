@@ -61,6 +61,58 @@ class ParamArena:
             ops.cast_f32_to_bf16(self.flat, self.shadow)
 
 
+class GradBuckets:
+    """Bucketed gradient all-reduce over the flat arena.  The arena is laid out in
+    backward-completion order (fc, decoder layers top-down, encoder layers top-down, embedding),
+    so each bucket is ONE contiguous slice that becomes final at a known point of the backward
+    pass; `ready(prefix)` is called from _Run.backward and launches the all-reduce of every
+    bucket whose groups are all final -- on `comm_stream` (NCCL) so it overlaps the remaining
+    backward kernels, or inline (gloo, CPU tests)."""
+
+    def __init__(self, model: ScoreTransformer, arena: GradArena, n_buckets: int, process_group, comm_stream=None):
+        self.arena, self.pg, self.comm_stream = arena, process_group, comm_stream
+        nd, ne = len(model.transformer.decoder.layers), len(model.transformer.encoder.layers)
+        groups = ["fc.", "transformer.decoder.norm."]          # == GradArena.order == signalling order
+        groups += [f"transformer.decoder.layers.{i}." for i in reversed(range(nd))]
+        groups += ["transformer.encoder.norm."]
+        groups += [f"transformer.encoder.layers.{i}." for i in reversed(range(ne))]
+        groups += ["embedding."]
+        self.groups = groups
+        spans = {g: arena.span(g) for g in groups}
+        per = max(1, math.ceil(len(groups) / max(1, n_buckets)))
+        self.buckets = []
+        for i in range(0, len(groups), per):
+            chunk = groups[i:i + per]
+            self.buckets.append((chunk, min(spans[g][0] for g in chunk), max(spans[g][1] for g in chunk)))
+        self.reset()
+
+    def reset(self):
+        self._done, self._launched, self.launch_order = set(), set(), []
+
+    def ready(self, prefix: str):
+        import torch.distributed as dist
+        self._done.add(prefix)
+        for idx, (chunk, b, e) in enumerate(self.buckets):
+            if idx in self._launched or not all(g in self._done for g in chunk):
+                continue
+            self._launched.add(idx)
+            self.launch_order.append(idx)
+            view = self.arena.flat[b:e]
+            if self.comm_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+            else:
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def finish(self):
+        assert len(self._launched) == len(self.buckets), "a gradient bucket was never signalled"
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
 class TrainEngine:
     def __init__(self, model: ScoreTransformer, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  eos_weight: float = 0.8, control_list: Sequence[str] = CONTROL_NAMES, process_group=None,
@@ -84,48 +136,7 @@ class TrainEngine:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
         self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
-        self._pending = []
-        self._bucket_bounds = self._make_buckets(n_buckets)
-        self._done_prefixes: List[str] = []
-        self.last_launches = 0
-
-    # ---- gradient buckets -------------------------------------------------------------
-    def _make_buckets(self, n: int):
-        """Splits the arena (already in backward-completion order) into ~n contiguous ranges
-        ending on layer boundaries; returns [(last_prefix_of_bucket, begin, end)]."""
-        m = self.model
-        groups = ["fc."]
-        nd, ne = len(m.transformer.decoder.layers), len(m.transformer.encoder.layers)
-        groups += [f"transformer.decoder.layers.{i}." for i in reversed(range(nd))]
-        groups += ["transformer.decoder.norm."]
-        groups += [f"transformer.encoder.layers.{i}." for i in reversed(range(ne))]
-        groups += ["transformer.encoder.norm.", "embedding."]
-        # completion order in _Run.backward: fc, dec layers (top-down), decoder.norm is signalled
-        # after the decoder loop, encoder layers, then encoder.norm + embedding at the very end.
-        spans = {g: self.grads.span(g) for g in groups}
-        self._spans = spans
-        per = max(1, math.ceil(len(groups) / max(1, n)))
-        buckets = []
-        for i in range(0, len(groups), per):
-            chunk = groups[i:i + per]
-            buckets.append((chunk, min(spans[g][0] for g in chunk), max(spans[g][1] for g in chunk)))
-        return buckets
-
-    def _grad_hook(self, prefix: str):
-        """Called by _Run.backward when every gradient of `prefix` has been written."""
-        import torch.distributed as dist
-        self._done_prefixes.append(prefix)
-        done = set(self._done_prefixes)
-        for chunk, b, e in self._bucket_bounds:
-            key = (b, e)
-            if key in self._launched or not all(g in done for g in chunk):
-                continue
-            self._launched.add(key)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
-                dist.all_reduce(self.grads.flat[b:e], op=dist.ReduceOp.SUM, group=self.pg)
+        self.buckets = GradBuckets(model, self.grads, n_buckets, process_group, self.comm_stream) if self.world > 1 else None
 
     # ---- one step ---------------------------------------------------------------------
     def step(self, src, tgt_in, tgt_out, src_pad=None, tgt_pad=None, update: bool = True):
@@ -153,15 +164,15 @@ class TrainEngine:
         dl = torch.empty(B * T, vp, dtype=m.compute_dtype, device=self.dev)
         ops.xent_bwd(logits, tg, self.W, lse, self.sums, dl, V, 1.0)
         self.grads.flat.zero_()
-        if self.world > 1:
-            self._done_prefixes, self._launched = [], set()
-            m.grad_hook = self._grad_hook
+        if self.buckets is not None:
+            self.buckets.reset()
+            m.grad_hook = self.buckets.ready
         try:
             run.backward(dl, self.grads.views)
         finally:
             m.grad_hook = None
-        if self.world > 1:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self.buckets is not None:
+            self.buckets.finish()
         if update:
             self.adam()
         return self.sums
