@@ -104,8 +104,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG: stateless, so backward regenerates the forward's dropout mask
-// from (seed, site offset, element index) instead of storing it.
+// Philox4x32-10 counter RNG (used by the sampler, where stream quality matters).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -123,14 +122,24 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint
 }
 
 // keep-mask for 4 consecutive elements starting at element index `idx4*4` of dropout site
-// `site`: returns per-element multiplier (0 or 1/(1-p)).  thr = p * 2^32.
+// `site`: per-element multiplier (0 or 1/(1-p)).  Counter hash, not Philox: Philox4x32-10 is
+// ~100 instructions per 4 elements, which made the GEMM/LayerNorm epilogues ALU-bound; two
+// avalanche mixes of (seed, site, index) give four 16-bit uniforms for ~16 instructions.
+// `thr` = p * 2^32 (dropout_threshold); the compare uses its top 16 bits.
+__device__ __forceinline__ uint32_t lowbias32_(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+  return x;
+}
 __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t site, uint64_t idx4, uint32_t thr,
                                          float inv_keep, float (&m)[4]) {
-  uint4 r = philox4x32(seed, idx4, site);
-  m[0] = r.x >= thr ? inv_keep : 0.f;
-  m[1] = r.y >= thr ? inv_keep : 0.f;
-  m[2] = r.z >= thr ? inv_keep : 0.f;
-  m[3] = r.w >= thr ? inv_keep : 0.f;
+  const uint32_t key = lowbias32_((uint32_t)seed ^ ((uint32_t)site * 0x9E3779B9u)) + (uint32_t)(seed >> 32);
+  const uint32_t a = lowbias32_(key ^ (uint32_t)idx4) + (uint32_t)(idx4 >> 32) * 0x85EBCA6Bu;
+  const uint32_t b0 = lowbias32_(a), b1 = lowbias32_(a ^ 0x68E31DA4u);
+  const uint32_t t16 = thr >> 16;
+  m[0] = (b0 & 0xFFFFu) >= t16 ? inv_keep : 0.f;
+  m[1] = (b0 >> 16) >= t16 ? inv_keep : 0.f;
+  m[2] = (b1 & 0xFFFFu) >= t16 ? inv_keep : 0.f;
+  m[3] = (b1 >> 16) >= t16 ? inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -80,11 +80,11 @@ gemm_simt_kernel(const TA* __restrict__ A, long long sam, long long sak, const T
         continue;
       }
       if (thr) {
-        // element-indexed Philox: lane k of counter (row*ldc + col)/4
+        // element-indexed keep mask: lane (e & 3) of dropout4 at counter (row*ldc + col)/4
         long long e = (long long)gm * ldc + gn;
-        uint4 r = philox4x32(seed, (uint64_t)(e >> 2), site);
-        uint32_t rr = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-        v = rr >= thr ? v * inv_keep : 0.f;
+        float m4[4];
+        dropout4(seed, site, (uint64_t)(e >> 2), thr, inv_keep, m4);
+        v *= m4[e & 3];
       }
       if (resid) v += to_f32(resid[(long long)gm * ldr + gn]);
       if (flags & SMER_EPI_ACCUM) v += to_f32(C[(long long)gm * ldc + gn]);

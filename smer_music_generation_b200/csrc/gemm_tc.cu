@@ -23,6 +23,30 @@ constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB per operan
 constexpr int GEMM_THREADS = 192;
 constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 t;
+  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
 struct EpiParams {
   void* C;
   long long ldc;
@@ -133,57 +157,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::tmem_ld_wait();
       if (!row_ok) continue;
 #pragma unroll
-      for (int g = 0; g < 32; g += 4) {
+      for (int g = 0; g < 32; g += 8) {           // 8 columns per step: 16-byte (bf16) / 2x16-byte (fp32) accesses
         const int col = n0 + c0 + g;
-        if (col >= p.N) break;
-        float v[4];
+        if (col >= p.N) break;                    // N % 8 == 0
+        float v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(r[g + u]);
+        for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[g + u]);
         if (p.flags & SMER_EPI_ATOMIC) {
           if (p.bias && blockIdx.z == 0) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] += p.bias[col + u];
+            for (int u = 0; u < 8; ++u) v[u] += p.bias[col + u];
           }
           float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                        "f"(v[3])
                        : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                       "f"(v[7])
+                       : "memory");
           continue;
         }
         if (p.bias) {
-          float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
-          v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
         if (p.flags & SMER_EPI_RELU) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = fmaxf(v[u], 0.f);
+          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
         }
         if (p.flags & SMER_EPI_GATE) {
-          float gte[4];
-          load4(rrow + col, gte);
+          float gte[8];
+          load8(rrow + col, gte);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
+          for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
         } else {
           if (p.thr) {
-            float m[4];
-            dropout4(p.seed, p.site, (uint64_t)(((long long)row * p.ldc + col) >> 2), p.thr, p.inv_keep, m);
+            float m0[4], m1[4];
+            const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
+            dropout4(p.seed, p.site, e4, p.thr, p.inv_keep, m0);
+            dropout4(p.seed, p.site, e4 + 1, p.thr, p.inv_keep, m1);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] *= m[u];
+            for (int u = 0; u < 4; ++u) { v[u] *= m0[u]; v[4 + u] *= m1[u]; }
           }
           if (rrow) {
-            float rs[4];
-            load4(rrow + col, rs);
+            float rs[8];
+            load8(rrow + col, rs);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] += rs[u];
+            for (int u = 0; u < 8; ++u) v[u] += rs[u];
           }
           if (p.flags & SMER_EPI_ACCUM) {
-            float old[4];
-            load4(crow + col, old);
+            float old[8];
+            load8(crow + col, old);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] += old[u];
+            for (int u = 0; u < 8; ++u) v[u] += old[u];
           }
         }
-        store4(crow + col, v);
+        store8(crow + col, v);
       }
     }
   }
@@ -285,7 +316,8 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
                                  const void* resid, long long ldr, int flags, float dropout_p, uint64_t seed,
                                  uint64_t site, int split_k, void* stream) {
   SMER_CHECK_ARG(M > 0 && N > 0 && K > 0, "smer_gemm_bf16_tc: empty problem %dx%dx%d", M, N, K);
-  SMER_CHECK_ARG(N % 8 == 0 && ldc % 4 == 0, "smer_gemm_bf16_tc: need N%%8==0 and ldc%%4==0 (N=%d ldc=%lld)", N, ldc);
+  SMER_CHECK_ARG(N % 8 == 0 && ldc % 8 == 0 && (!resid || ldr % 8 == 0),
+                 "smer_gemm_bf16_tc: need N%%8==0 and 8-element-aligned C/resid pitches (N=%d ldc=%lld ldr=%lld)", N, ldc, ldr);
   if (split_k < 1) split_k = 1;
   SMER_CHECK_ARG(split_k == 1 || ((flags & SMER_EPI_ATOMIC) && out_dtype == SMER_DT_F32),
                  "smer_gemm_bf16_tc: split_k needs SMER_EPI_ATOMIC and fp32 output");

@@ -86,7 +86,7 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dropout_
 
 
 def _tc_ok(a_dtype, N, ldc, *pitches):
-    return (_TC_GEMM == "tc" and a_dtype == torch.bfloat16 and N % 8 == 0 and ldc % 4 == 0
+    return (_TC_GEMM == "tc" and a_dtype == torch.bfloat16 and N % 8 == 0 and ldc % 8 == 0
             and all(p % 8 == 0 for p in pitches))
 
 
@@ -97,7 +97,7 @@ def gemm_nt(A, W, out, bias=None, resid=None, flags=0, dropout_p=0.0, seed=0, si
         N = W.shape[0]
         lda, ldw, ldc = A.stride(0), W.stride(0), out.stride(0)
         ldr = resid.stride(0) if resid is not None else 0
-        if _tc_ok(A.dtype, N, ldc, lda, ldw):
+        if _tc_ok(A.dtype, N, ldc, lda, ldw, ldr):
             K.check(K.lib().smer_gemm_bf16_tc(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(out), M, N, Kd, _p(bias),
                                               _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()), "gemm_tc(nt)")
         else:
@@ -113,7 +113,7 @@ def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0):
         Kin = W.shape[1]
         ldy, ldw, ldc = dY.stride(0), W.stride(0), out.stride(0)
         ldr = resid.stride(0) if resid is not None else 0
-        if _tc_ok(dY.dtype, Kin, ldc, ldy, ldw):
+        if _tc_ok(dY.dtype, Kin, ldc, ldy, ldw, ldr):
             K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 1, _p(W), ldw, 0, _p(out), ldc, K.dt(out), M, Kin, N, 0,
                                               _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_tc(dx)")
         else:
