@@ -5,10 +5,13 @@
 // MultiheadAttention in/out projections, model.py:82 fc) and both backward products
 // (dX = dY.W uses B MN-major; dW = dY^T.X uses A and B MN-major with split-K fp32 atomics).
 //
-// CTA = 128x128 output tile, K step 64, 3-stage ring (96 KB) so two CTAs share an SM and one
-// CTA's epilogue overlaps the other's main loop; 128 TMEM columns per CTA.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue (TMEM lane
-// quarter = warp_idx % 4).
+// Persistent: one CTA per SM walks a static list of (128x128 tile, K-split) work items, N fastest
+// so that concurrently running CTAs share A rows in L2.  K step 64, 6-stage smem ring (192 KB)
+// that keeps filling across work items; TWO 128-column fp32 accumulators in TMEM so the epilogue
+// of item i (8 warps: TMEM -> registers -> bias/ReLU/dropout/residual/gate -> 16-byte global
+// stores, or fp32 split-K reductions) overlaps the MMAs of item i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue (TMEM lane quarter
+// = warp_idx % 4, column half = (warp_idx - 2) / 4).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/smer_b200.h"
@@ -18,10 +21,11 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
 constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB per operand per stage
-constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // 197,888 B
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -59,10 +63,11 @@ struct EpiParams {
   float inv_keep;
   uint64_t seed, site;
   int kb_per_split, num_kb;
+  int tiles_m, tiles_n, splits;          // work item w -> (split, m tile, n tile), n fastest
 };
 
 template <bool A_MN, bool B_MN, typename TC>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -70,14 +75,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* sB = smem + STAGES * TILE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGES * TILE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-  const int nkb = kb1 - kb0;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total = tiles_mn * p.splits;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -86,10 +90,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_init(full_bar + s, 1);
       ptx::mbar_init(empty_bar + s, 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tmem_full_bar + a, 1);
+      ptx::mbar_init(tmem_empty_bar + a, EPI_WARPS);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<128>(tmem_ptr);
+  if (warp == 1) ptx::tmem_alloc<256>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -97,24 +104,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        ptx::mbar_wait(empty_bar + s, ((i / STAGES) & 1) ^ 1);
-        ptx::mbar_expect_tx(full_bar + s, 2 * TILE_BYTES);
-        const int k = (kb0 + i) * BK;
-        uint8_t* a = sA + s * TILE_BYTES;
-        uint8_t* b = sB + s * TILE_BYTES;
-        if (!A_MN) {
-          ptx::tma_load_2d(a, &tmap_a, full_bar + s, k, m0);
-        } else {
-          ptx::tma_load_2d(a, &tmap_a, full_bar + s, m0, k);
-          ptx::tma_load_2d(a + TILE_BYTES / 2, &tmap_a, full_bar + s, m0 + 64, k);
-        }
-        if (!B_MN) {
-          ptx::tma_load_2d(b, &tmap_b, full_bar + s, k, n0);
-        } else {
-          ptx::tma_load_2d(b, &tmap_b, full_bar + s, n0, k);
-          ptx::tma_load_2d(b + TILE_BYTES / 2, &tmap_b, full_bar + s, n0 + 64, k);
+      int it = 0;                                            // global k-block counter -> ring slot / parity
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
+        const int m0 = (rem / p.tiles_n) * BM, n0 = (rem % p.tiles_n) * BN;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);
+          ptx::mbar_expect_tx(full_bar + s, 2 * TILE_BYTES);
+          const int k = kb * BK;
+          uint8_t* a = sA + s * TILE_BYTES;
+          uint8_t* b = sB + s * TILE_BYTES;
+          if (!A_MN) {
+            ptx::tma_load_2d(a, &tmap_a, full_bar + s, k, m0);
+          } else {
+            ptx::tma_load_2d(a, &tmap_a, full_bar + s, m0, k);
+            ptx::tma_load_2d(a + TILE_BYTES / 2, &tmap_a, full_bar + s, m0 + 64, k);
+          }
+          if (!B_MN) {
+            ptx::tma_load_2d(b, &tmap_b, full_bar + s, k, n0);
+          } else {
+            ptx::tma_load_2d(b, &tmap_b, full_bar + s, n0, k);
+            ptx::tma_load_2d(b + TILE_BYTES / 2, &tmap_b, full_bar + s, n0 + 64, k);
+          }
         }
       }
     }
@@ -122,105 +135,127 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        ptx::mbar_wait(full_bar + s, (i / STAGES) & 1);
+      int it = 0, item = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++item) {
+        const int sp = w / tiles_mn;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int acc = item & 1;
+        ptx::mbar_wait(tmem_empty_bar + acc, ((item >> 1) & 1) ^ 1);     // epilogue drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t a = ptx::smem_u32(sA + s * TILE_BYTES);
-        const uint32_t b = ptx::smem_u32(sB + s * TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(full_bar + s, (it / STAGES) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a = ptx::smem_u32(sA + s * TILE_BYTES);
+          const uint32_t b = ptx::smem_u32(sB + s * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 16 elements = 32 B inside the 128 B swizzle row; rows 8 apart are 1024 B apart.
-          // MN-major: 16 k-rows = 2048 B; 64-element MN chunks are 8192 B apart, 8-row groups 1024 B.
-          const uint64_t ad = A_MN ? ptx::make_smem_desc(a + k * 2048, 8192, 1024) : ptx::make_smem_desc(a + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? ptx::make_smem_desc(b + k * 2048, 8192, 1024) : ptx::make_smem_desc(b + k * 32, 16, 1024);
-          ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 elements = 32 B inside the 128 B swizzle row; rows 8 apart are 1024 B apart.
+            // MN-major: 16 k-rows = 2048 B; 64-element MN chunks are 8192 B apart, 8-row groups 1024 B.
+            const uint64_t ad = A_MN ? ptx::make_smem_desc(a + k * 2048, 8192, 1024) : ptx::make_smem_desc(a + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? ptx::make_smem_desc(b + k * 2048, 8192, 1024) : ptx::make_smem_desc(b + k * 32, 16, 1024);
+            ptx::umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar + s);        // frees the smem stage once these MMAs have read it
         }
-        ptx::umma_commit(empty_bar + s);        // frees the smem stage once these MMAs have read it
+        ptx::umma_commit(tmem_full_bar + acc);    // accumulator complete
       }
-      ptx::umma_commit(tmem_full_bar);          // accumulator complete
     }
     __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < p.M;
-    TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
-    const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, r);
+    const int chalf = (warp - 2) >> 2;              // which 64 of the tile's 128 columns
+    int item = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++item) {
+      const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
+      const int m0 = (rem / p.tiles_n) * BM, n0 = (rem % p.tiles_n) * BN;
+      const int acc = item & 1;
+      ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
+      ptx::tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
+      const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * 64;
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld_32x32(t_addr, r0);
+      ptx::tmem_ld_32x32(t_addr + 32, r1);
       ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);   // accumulator is in registers: MMA may reuse it
       if (!row_ok) continue;
 #pragma unroll
-      for (int g = 0; g < 32; g += 8) {           // 8 columns per step: 16-byte (bf16) / 2x16-byte (fp32) accesses
-        const int col = n0 + c0 + g;
-        if (col >= p.N) break;                    // N % 8 == 0
-        float v[8];
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t* r = hh == 0 ? r0 : r1;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[g + u]);
-        if (p.flags & SMER_EPI_ATOMIC) {
-          if (p.bias && blockIdx.z == 0) {
+        for (int g = 0; g < 32; g += 8) {           // 8 columns per step: 16-byte (bf16) / 2x16-byte (fp32) accesses
+          const int col = n0 + chalf * 64 + hh * 32 + g;
+          if (col >= p.N) break;                    // N % 8 == 0
+          float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += p.bias[col + u];
+          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[g + u]);
+          if (p.flags & SMER_EPI_ATOMIC) {
+            if (p.bias && sp == 0) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] += p.bias[col + u];
+            }
+            float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                         "f"(v[3])
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                         "f"(v[7])
+                         : "memory");
+            continue;
           }
-          float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                       "f"(v[3])
-                       : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
-                       "f"(v[7])
-                       : "memory");
-          continue;
-        }
-        if (p.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (p.flags & SMER_EPI_RELU) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
-        }
-        if (p.flags & SMER_EPI_GATE) {
-          float gte[8];
-          load8(rrow + col, gte);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
-        } else {
-          if (p.thr) {
-            float m0[4], m1[4];
-            const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
-            dropout4(p.seed, p.site, e4, p.thr, p.inv_keep, m0);
-            dropout4(p.seed, p.site, e4 + 1, p.thr, p.inv_keep, m1);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { v[u] *= m0[u]; v[4 + u] *= m1[u]; }
+          if (p.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
-          if (rrow) {
-            float rs[8];
-            load8(rrow + col, rs);
+          if (p.flags & SMER_EPI_RELU) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += rs[u];
+            for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
           }
-          if (p.flags & SMER_EPI_ACCUM) {
-            float old[8];
-            load8(crow + col, old);
+          if (p.flags & SMER_EPI_GATE) {
+            float gte[8];
+            load8(rrow + col, gte);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += old[u];
+            for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
+          } else {
+            if (p.thr) {
+              float m0_[4], m1_[4];
+              const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
+              dropout4(p.seed, p.site, e4, p.thr, p.inv_keep, m0_);
+              dropout4(p.seed, p.site, e4 + 1, p.thr, p.inv_keep, m1_);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
+            }
+            if (rrow) {
+              float rs[8];
+              load8(rrow + col, rs);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] += rs[u];
+            }
+            if (p.flags & SMER_EPI_ACCUM) {
+              float old[8];
+              load8(crow + col, old);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] += old[u];
+            }
           }
+          store8(crow + col, v);
         }
-        store8(crow + col, v);
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<128>(tmem_base);
+  if (warp == 1) ptx::tmem_dealloc<256>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -340,7 +375,12 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   if (split_k > p.num_kb) split_k = p.num_kb;
   p.kb_per_split = (p.num_kb + split_k - 1) / split_k;
   split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;       // no empty splits
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
+  p.tiles_n = (N + BN - 1) / BN;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.splits = split_k;
+  const long long total = (long long)p.tiles_n * p.tiles_m * split_k;
+  const int sms = smer_num_sms();
+  dim3 grid((unsigned)(total < sms ? total : sms));
   cudaStream_t st = (cudaStream_t)stream;
   const bool amn = !a_kmajor, bmn = !b_kmajor, f32 = out_dtype == SMER_DT_F32;
 #define GO(AM, BMN, T) rc = launch_gemm<AM, BMN, T>(ta, tb, p, grid, st)
