@@ -207,9 +207,19 @@ def run_train(args):
         dist.all_reduce(t)
         return float(t.item())
 
+    use_graph = world == 1 and not args.no_graph
+    launches_per_step = None
+    if use_graph:
+        l0 = ops.LAUNCHES
+        eng.capture(B, S, T)                              # warm-up step + capture (two passes of launches)
+        launches_per_step = (ops.LAUNCHES - l0) // 2 + 3  # + arena memset, loss-sum memset, counter bump
+        step = lambda b: eng.step_graph(*b)
+    else:
+        step = lambda b: eng.step(*b)
+
     # ---- device-resident ("value") ----
     for i in range(args.warmup):
-        eng.step(*devb[i % nb])
+        step(devb[i % nb])
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = ops.LAUNCHES
@@ -217,12 +227,15 @@ def run_train(args):
     e0.record()
     toks = 0
     for i in range(args.steps):
-        eng.step(*devb[i % nb])
+        step(devb[i % nb])
         toks += ntok[i % nb]
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ops.LAUNCHES - l0 + 2 * args.steps          # + arena memset + loss-sum memset per step
+    if use_graph:
+        launches = launches_per_step * args.steps         # kernels in the captured step x replays
+    else:
+        launches = ops.LAUNCHES - l0 + 2 * args.steps      # + arena memset + loss-sum memset per step
     clk = clocks.stop() if clocks else None
     total_toks = sum_over_ranks(toks)
     value = total_toks / (ms * 1e-3)
@@ -232,17 +245,23 @@ def run_train(args):
     barrier()
     e0.record()
     toks2 = 0
+    loss_host = torch.zeros(args.steps, 16, dtype=torch.float64).pin_memory()
     for i in range(args.steps):
-        b = tuple(t.to(dev, non_blocking=True) for t in host[i % nb])
-        eng.step(*b)
-        _ = eng.loss_value()                             # D2H of the 16 loss sums (128 B) + sync
+        if use_graph:
+            eng.step_graph(*host[i % nb])                # pinned host batch -> H2D into the step's input buffers
+        else:
+            eng.step(*tuple(t.to(dev, non_blocking=True) for t in host[i % nb]))
+        loss_host[i].copy_(eng.sums, non_blocking=True)  # D2H of the step's 16 loss sums (128 B), every step
         toks2 += ntok[i % nb]
     e1.record()
-    barrier()
+    barrier()                                            # all losses have landed on the host here
+    assert bool(torch.isfinite(loss_host[:, 0] / loss_host[:, 1]).all())
     ms2 = max_over_ranks(e0.elapsed_time(e1))
     e2e = sum_over_ranks(toks2) / (ms2 * 1e-3)
 
     # ---- per-kernel-family timing pass (events around every launch; not part of `value`) ----
+    if use_graph:
+        eng.release_graph()
     ops.PROFILE = {}
     eng.step(*devb[0])
     torch.cuda.synchronize()
@@ -282,10 +301,11 @@ def run_train(args):
                                        f"train step fwd+loss+bwd+Adam, dropout 0.1, B{B}/GPU x S{S} (+T{T}), suffix padding "
                                        f"U[0.75L,L], tokens counted = non-pad src+tgt",
                            "l2": "working set per step (~3.5 GB activations) >> 126 MB L2; 4 rotating input batches",
-                           "parallelism": f"dp{world}", "global_batch": B * world},
+                           "parallelism": f"dp{world}", "global_batch": B * world,
+                           "launch": "whole step captured in one CUDA graph, replayed per step" if use_graph else "eager launches"},
                 "clocks": clk,
                 "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 128,
-                        "ms_per_step": ms2 / args.steps, "api": "TrainEngine.step over ScoreTransformer (pinned host batch in, loss out)"},
+                        "ms_per_step": ms2 / args.steps, "api": "TrainEngine.step_graph/step over ScoreTransformer (pinned host batch in, loss sums out, async D2H every step)"},
                 "gpu_launches": launches,
                 "roofline": roof,
                 "cpu_baseline": cpu,
@@ -379,6 +399,7 @@ def main():
     ap.add_argument("--decode-len", type=int, default=512)
     ap.add_argument("--splits", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and args.workload == "train":
         args.warmup = max(args.warmup, 1)

@@ -51,6 +51,9 @@ int smer_version(void);
 const char* smer_last_error(void);
 /* 1 when the running device is compute capability 10.x (sm_100a cubins loadable) */
 int smer_device_ok(void);
+/* Device uint64 added to every dropout seed at kernel run time (NULL = off).  A training step
+ * captured into a CUDA graph bumps this counter inside the graph, so replays draw new masks. */
+int smer_set_seed_device_ptr(const uint64_t* dev_counter);
 
 /* ---- K1: embedding * sqrt(d) + sinusoidal PE (+dropout).  model.py:91-92, 123-125 ---------- */
 int smer_embed_pe_fwd(const int64_t* ids, const float* emb, const float* pe, void* out, int out_dtype,
@@ -124,6 +127,10 @@ int smer_xent_bwd(const float* logits, long long ld, const int64_t* targets, con
 /* ---- K11: Adam.  train.py:264,786 ------------------------------------------------------------ */
 int smer_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
                    float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* same update with the step number read from device memory (CUDA-graph replays) */
+int smer_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
+                       const uint64_t* step_dev, float lr, float beta1, float beta2, float eps, float grad_scale,
+                       void* stream);
 
 /* ---- K12: decode step.  generation.py:209-225 (model call), 41-95 + 538-686 (sampling) ------- */
 typedef struct smer_decode_attn_args {

@@ -52,6 +52,7 @@ _SIGS = {
     "smer_version": (C.c_int, []),
     "smer_last_error": (C.c_char_p, []),
     "smer_device_ok": (C.c_int, []),
+    "smer_set_seed_device_ptr": (_i, [_vp]),
     "smer_embed_pe_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _u64, _vp]),
     "smer_embed_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _f, _u64, _u64, _vp]),
     "smer_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _f, _u64, _u64, _vp]),
@@ -69,6 +70,7 @@ _SIGS = {
     "smer_xent_fwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _vp]),
     "smer_xent_bwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _vp, _vp]),
     "smer_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _f, _f, _f, _f, _vp]),
+    "smer_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _f, _vp]),
     "smer_decode_attn_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "smer_decode_attn": (_i, [C.POINTER(DecodeAttnArgs), _vp]),
     "smer_decode_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

@@ -31,6 +31,7 @@ struct AttnParams {
   uint32_t thr;
   float inv_keep;
   uint64_t seed, site;
+  const unsigned long long* seed_dev;
 };
 
 template <int DPT, int TPR>
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
-  const uint32_t rowkey = p.thr ? attn_row_key(p.seed, p.site, rowid) : 0u;
+  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
   const T* vb = (const T*)p.v + (long long)b * p.Lk * p.ldv + h * DH;
 
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
   }
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
   float lse = p.lse[rowid], dsum = p.dsum[rowid];
-  const uint32_t rowkey = p.thr ? attn_row_key(p.seed, p.site, rowid) : 0u;
+  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(AttnParams p) {
       float pr = masked ? 0.f : expf(s - Ls[ii]);
       float dmv = 1.f;
       if (p.thr)
-        dmv = attn_keep(attn_row_key(p.seed, p.site, rowbase + min(i, p.Lq - 1)), jc, p.thr) ? p.inv_keep : 0.f;
+        dmv = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + min(i, p.Lq - 1)), jc, p.thr) ? p.inv_keep : 0.f;
       float dp = row_dot<DPT, TPR>(vr, &Gs[ii][part * DPT]) * dmv;
       float ds = pr * (dp - Ds[ii]);
       float pd = pr * dmv;
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_weights_kernel(AttnParams p, fl
         if (p.addmask) s += p.addmask[(long long)i * p.ldmask + j];
         long long rowid = ((long long)b * p.H + h) * p.Lq + i;
         float pr = expf(s - p.lse[rowid]);
-        if (p.thr) pr = attn_keep(attn_row_key(p.seed, p.site, rowid), j, p.thr) ? pr * p.inv_keep : 0.f;
+        if (p.thr) pr = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid), j, p.thr) ? pr * p.inv_keep : 0.f;
         acc += pr;
       }
     }
@@ -387,7 +388,7 @@ static int fill_params(AttnParams& p, const smer_attn_args* a, const char* who) 
   p.scale = a->scale; p.causal = a->causal; p.q_pos0 = a->q_pos0;
   p.thr = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;      // 16-bit threshold
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
-  p.seed = a->seed; p.site = a->site;
+  p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   if (p.B <= 0 || p.H <= 0 || p.Lq <= 0 || p.Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }
   return SMER_OK;
 }

@@ -42,6 +42,7 @@ struct FwdParams {
   uint32_t thr16;
   float inv_keep;
   uint64_t seed, site;
+  const unsigned long long* seed_dev;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -144,7 +145,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t sP_row = ptx::smem_u32(sP) + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
     const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
-    const uint32_t rowkey = p.thr16 ? attn_row_key(p.seed, p.site, rowid) : 0u;
+    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
     const float c2 = p.c_log2;
     float m = -INFINITY, l = 0.f;
     float acc[DH];
@@ -291,6 +292,7 @@ struct BwdParams {
   uint32_t thr16;
   float inv_keep;
   uint64_t seed, site;
+  const unsigned long long* seed_dev;
 };
 
 // 8 consecutive bf16 of row `r` (16-byte chunk c16 of a 128-byte SWIZZLE_128B row)
@@ -418,7 +420,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t row_addr = ptx::smem_u32(sdS) + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
     const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
-    const uint32_t rowkey = p.thr16 ? attn_row_key(p.seed, p.site, rowid) : 0u;
+    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
     float lse2 = INFINITY, dsum = 0.f;
     if (row_ok) {
       const float l = p.lse[rowid];
@@ -618,7 +620,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const float l = p.lse[rowbase + i];
           l2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
           ds_ = p.dsum[rowbase + i];
-          if (p.thr16) rk = attn_row_key(p.seed, p.site, rowbase + i);
+          if (p.thr16) rk = attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + i);
         }
         s_lse[slot + r] = l2;
         s_dsum[slot + r] = ds_;
@@ -725,7 +727,7 @@ extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
   p.causal = a->causal;
   p.thr16 = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
-  p.seed = a->seed; p.site = a->site;
+  p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   static bool attr_set = false;
   if (!attr_set) {
     SMER_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
@@ -759,7 +761,7 @@ extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   p.c_log2 = a->scale * 1.4426950408889634f; p.scale = a->scale; p.causal = a->causal;
   p.thr16 = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
-  p.seed = a->seed; p.site = a->site;
+  p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   static bool attr_set = false;
   if (!attr_set) {
     SMER_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));

@@ -24,6 +24,13 @@ int smer_num_sms() {
   return cached;
 }
 
+static const unsigned long long* g_seed_dev = nullptr;
+const unsigned long long* smer_seed_dev() { return g_seed_dev; }
+extern "C" int smer_set_seed_device_ptr(const uint64_t* p) {
+  g_seed_dev = reinterpret_cast<const unsigned long long*>(p);
+  return SMER_OK;
+}
+
 extern "C" int smer_version(void) { return SMER_B200_VERSION; }
 extern "C" const char* smer_last_error(void) { return g_err; }
 

@@ -46,6 +46,12 @@ void smer_set_error(const char* fmt, ...);
   } while (0)
 
 int smer_num_sms();
+// Optional device-resident addend for every dropout seed (smer_set_seed_device_ptr): lets a
+// captured CUDA graph draw fresh masks on every replay.  NULL when unset.
+const unsigned long long* smer_seed_dev();
+__device__ __forceinline__ uint64_t eff_seed(uint64_t seed, const unsigned long long* seed_dev) {
+  return seed_dev ? seed + *seed_dev : seed;
+}
 
 // ---------------------------------------------------------------------------------------
 // element conversion

@@ -11,7 +11,8 @@ template <typename T>
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
                                     const float* __restrict__ pe, T* __restrict__ out, long long n4,
                                     int L, int d4, int V, int pos0, float scale, uint32_t thr, float inv_keep,
-                                    uint64_t seed, uint64_t site) {
+                                    uint64_t seed, uint64_t site, const unsigned long long* seed_dev) {
+  seed = eff_seed(seed, seed_dev);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     long long row = i / d4;
@@ -38,7 +39,9 @@ __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float
 template <typename T>
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ ids, const T* __restrict__ dout,
                                  float* __restrict__ demb, long long n4, int d4, int V, float scale,
-                                 uint32_t thr, float inv_keep, uint64_t seed, uint64_t site) {
+                                 uint32_t thr, float inv_keep, uint64_t seed, uint64_t site,
+                                 const unsigned long long* seed_dev) {
+  seed = eff_seed(seed, seed_dev);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     long long row = i / d4;
@@ -78,9 +81,9 @@ extern "C" int smer_embed_pe_fwd(const int64_t* ids, const float* emb, const flo
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(n4, 256);
   if (out_dtype == SMER_DT_F32)
-    embed_pe_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, emb, pe, (float*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site);
+    embed_pe_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, emb, pe, (float*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site, smer_seed_dev());
   else
-    embed_pe_fwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, emb, pe, (bf16*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site);
+    embed_pe_fwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, emb, pe, (bf16*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site, smer_seed_dev());
   SMER_CHECK_LAUNCH("smer_embed_pe_fwd");
   return SMER_OK;
 }
@@ -95,9 +98,9 @@ extern "C" int smer_embed_bwd(const int64_t* ids, const void* dout, int dtype, f
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(n4, 256);
   if (dtype == SMER_DT_F32)
-    embed_bwd_kernel<float><<<grid, 256, 0, st>>>(ids, (const float*)dout, demb, n4, d / 4, V, scale, thr, inv_keep, seed, site);
+    embed_bwd_kernel<float><<<grid, 256, 0, st>>>(ids, (const float*)dout, demb, n4, d / 4, V, scale, thr, inv_keep, seed, site, smer_seed_dev());
   else
-    embed_bwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, (const bf16*)dout, demb, n4, d / 4, V, scale, thr, inv_keep, seed, site);
+    embed_bwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, (const bf16*)dout, demb, n4, d / 4, V, scale, thr, inv_keep, seed, site, smer_seed_dev());
   SMER_CHECK_LAUNCH("smer_embed_bwd");
   return SMER_OK;
 }
@@ -262,7 +265,13 @@ extern "C" int smer_classify_mask(const float* mask, long long ld, int T, int* f
 // ---------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, bf16* __restrict__ shadow, long long n4, float lr, float b1,
-                            float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+                            float b2, float eps, float bc1, float bc2_sqrt, float gscale,
+                            const unsigned long long* __restrict__ step_dev) {
+  if (step_dev) {                 // step number lives on the device (CUDA-graph replays advance it)
+    const float st = (float)(*step_dev);
+    bc1 = 1.f - powf(b1, st);
+    bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float pp[4], gg[4], mm[4], vv[4];
@@ -285,14 +294,28 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+static int adam_launch(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
+                       const uint64_t* step_dev, float lr, float beta1, float beta2, float eps, float grad_scale,
+                       void* stream) {
+  SMER_CHECK_ARG(n % 4 == 0 && (step >= 1 || step_dev), "smer_adam_step: n must be a multiple of 4 and step >= 1");
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, (bf16*)bf16_shadow, n / 4, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale,
+      reinterpret_cast<const unsigned long long*>(step_dev));
+  SMER_CHECK_LAUNCH("smer_adam_step");
+  return SMER_OK;
+}
+
 extern "C" int smer_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
                               int step, float lr, float beta1, float beta2, float eps, float grad_scale,
                               void* stream) {
-  SMER_CHECK_ARG(n % 4 == 0 && step >= 1, "smer_adam_step: n must be a multiple of 4 and step >= 1");
-  float bc1 = 1.f - powf(beta1, (float)step);
-  float bc2 = 1.f - powf(beta2, (float)step);
-  adam_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)bf16_shadow, n / 4, lr, beta1,
-                                                                   beta2, eps, bc1, sqrtf(bc2), grad_scale);
-  SMER_CHECK_LAUNCH("smer_adam_step");
-  return SMER_OK;
+  return adam_launch(p, g, m, v, bf16_shadow, n, step, nullptr, lr, beta1, beta2, eps, grad_scale, stream);
+}
+
+extern "C" int smer_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
+                                  const uint64_t* step_dev, float lr, float beta1, float beta2, float eps,
+                                  float grad_scale, void* stream) {
+  SMER_CHECK_ARG(step_dev != nullptr, "smer_adam_step_dev: null step pointer");
+  return adam_launch(p, g, m, v, bf16_shadow, n, 0, step_dev, lr, beta1, beta2, eps, grad_scale, stream);
 }

@@ -14,7 +14,9 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, long long sam, long long sak, const TA* __restrict__ B,
                  long long sbn, long long sbk, TC* __restrict__ C, long long ldc, int M, int N, int K,
                  const float* __restrict__ bias, const TC* __restrict__ resid, long long ldr, int flags,
-                 uint32_t thr, float inv_keep, uint64_t seed, uint64_t site, int ksplit_len) {
+                 uint32_t thr, float inv_keep, uint64_t seed, uint64_t site, int ksplit_len,
+                 const unsigned long long* seed_dev) {
+  seed = eff_seed(seed, seed_dev);
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   int tid = threadIdx.x;
@@ -112,7 +114,7 @@ extern "C" int smer_gemm_simt(const void* A, long long sam, long long sak, const
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(TA, TC)                                                                                              \
   gemm_simt_kernel<TA, TC><<<grid, 256, 0, st>>>((const TA*)A, sam, sak, (const TA*)B, sbn, sbk, (TC*)C, ldc, M, N, K, \
-                                                 bias, (const TC*)resid, ldr, flags, thr, inv_keep, seed, site, klen)
+                                                 bias, (const TC*)resid, ldr, flags, thr, inv_keep, seed, site, klen, smer_seed_dev())
   if (in_dtype == SMER_DT_F32 && out_dtype == SMER_DT_F32) LAUNCH(float, float);
   else if (in_dtype == SMER_DT_BF16 && out_dtype == SMER_DT_BF16) LAUNCH(bf16, bf16);
   else if (in_dtype == SMER_DT_BF16 && out_dtype == SMER_DT_F32) LAUNCH(bf16, float);

@@ -6,10 +6,12 @@
 // (dX = dY.W uses B MN-major; dW = dY^T.X uses A and B MN-major with split-K fp32 atomics).
 //
 // Persistent: one CTA per SM walks a static list of (128x128 tile, K-split) work items, N fastest
-// so that concurrently running CTAs share A rows in L2.  K step 64, 6-stage smem ring (192 KB)
+// so that concurrently running CTAs share A rows in L2.  K step 64, 4-stage smem ring (128 KB)
 // that keeps filling across work items; TWO 128-column fp32 accumulators in TMEM so the epilogue
-// of item i (8 warps: TMEM -> registers -> bias/ReLU/dropout/residual/gate -> 16-byte global
-// stores, or fp32 split-K reductions) overlaps the MMAs of item i+1.
+// of item i overlaps the MMAs of item i+1.  Epilogue (8 warps): TMEM -> registers -> per-warp smem
+// transpose (so that one store instruction covers 4 full 128-byte row segments instead of 32
+// scattered rows) -> bias/ReLU/dropout/residual/gate -> 16-byte global stores / fp32 split-K
+// reductions; residual and gate operands are read with the same coalesced mapping.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue (TMEM lane quarter
 // = warp_idx % 4, column half = (warp_idx - 2) / 4).
 #include "common.cuh"
@@ -21,11 +23,12 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
 constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB per operand per stage
 constexpr int GEMM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;   // 197,888 B
+constexpr int STAGE_EPI = 32 * 64 * 4;                        // per epilogue warp: 32 rows x 64 fp32 columns
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + EPI_WARPS * STAGE_EPI + 1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -51,6 +54,13 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = t;
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, float* v) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+}
+
 struct EpiParams {
   void* C;
   long long ldc;
@@ -62,6 +72,7 @@ struct EpiParams {
   uint32_t thr;
   float inv_keep;
   uint64_t seed, site;
+  const unsigned long long* seed_dev;
   int kb_per_split, num_kb;
   int tiles_m, tiles_n, splits;          // work item w -> (split, m tile, n tile), n fastest
 };
@@ -73,7 +84,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TILE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * STAGES * TILE_BYTES);
+  uint8_t* sEpi = smem + 2 * STAGES * TILE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + EPI_WARPS * STAGE_EPI);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -166,7 +178,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     const int quarter = warp & 3;
+    const uint64_t seed = (p.thr && !(p.flags & SMER_EPI_GATE)) ? eff_seed(p.seed, p.seed_dev) : 0ull;
     const int chalf = (warp - 2) >> 2;              // which 64 of the tile's 128 columns
+    const uint32_t stage_addr = ptx::smem_u32(sEpi + (warp - 2) * STAGE_EPI);
     int item = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++item) {
       const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
@@ -174,82 +188,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int acc = item & 1;
       ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
       ptx::tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
-      const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * 64;
       uint32_t r0[32], r1[32];
       ptx::tmem_ld_32x32(t_addr, r0);
       ptx::tmem_ld_32x32(t_addr + 32, r1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      __syncwarp();
+      __syncwarp();                                            // also: previous item's staging reads are done
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);   // accumulator is in registers: MMA may reuse it
-      if (!row_ok) continue;
+      // stage: lane == tile row; 16-byte chunk c of the 256-byte row goes to chunk c ^ (row & 15)
+      {
+        const uint32_t rowbase = stage_addr + lane * 256;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const uint32_t* r = hh == 0 ? r0 : r1;
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(rowbase + (((uint32_t)c ^ (lane & 15)) << 4), r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
 #pragma unroll
-        for (int g = 0; g < 32; g += 8) {           // 8 columns per step: 16-byte (bf16) / 2x16-byte (fp32) accesses
-          const int col = n0 + chalf * 64 + hh * 32 + g;
-          if (col >= p.N) break;                    // N % 8 == 0
-          float v[8];
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(rowbase + (((uint32_t)(c + 8) ^ (lane & 15)) << 4), r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
+      }
+      __syncwarp();
+      // drain: lane -> (row = it*4 + lane/8, 8 columns starting at (lane%8)*8): 4 rows x 128 B (bf16) per store
+      const int lc = (lane & 7) * 8;
+      const int col = n0 + chalf * 64 + lc;
+      if (col >= p.N) continue;                                // N % 8 == 0
+      float bias8[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[g + u]);
-          if (p.flags & SMER_EPI_ATOMIC) {
-            if (p.bias && sp == 0) {
-#pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] += p.bias[col + u];
-            }
-            float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                         "f"(v[3])
-                         : "memory");
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
-                         "f"(v[7])
-                         : "memory");
-            continue;
-          }
-          if (p.bias) {
-            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.flags & SMER_EPI_RELU) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
-          }
-          if (p.flags & SMER_EPI_GATE) {
-            float gte[8];
-            load8(rrow + col, gte);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
-          } else {
-            if (p.thr) {
-              float m0_[4], m1_[4];
-              const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
-              dropout4(p.seed, p.site, e4, p.thr, p.inv_keep, m0_);
-              dropout4(p.seed, p.site, e4 + 1, p.thr, p.inv_keep, m1_);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
-            }
-            if (rrow) {
-              float rs[8];
-              load8(rrow + col, rs);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] += rs[u];
-            }
-            if (p.flags & SMER_EPI_ACCUM) {
-              float old[8];
-              load8(crow + col, old);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] += old[u];
-            }
-          }
-          store8(crow + col, v);
+      for (int u = 0; u < 8; ++u) bias8[u] = 0.f;
+      if (p.bias && (!(p.flags & SMER_EPI_ATOMIC) || sp == 0)) load8(p.bias + col, bias8);
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + (lane >> 3);
+        const int row = m0 + quarter * 32 + rl;
+        if (row >= p.M) continue;
+        float v[8];
+        {
+          const uint32_t rowbase = stage_addr + rl * 256;
+          const uint32_t c0 = (uint32_t)(lc >> 2);
+          ld_shared_v4(rowbase + ((c0 ^ (rl & 15)) << 4), v);
+          ld_shared_v4(rowbase + (((c0 + 1) ^ (rl & 15)) << 4), v + 4);
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] += bias8[u];
+        TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
+        if (p.flags & SMER_EPI_ATOMIC) {
+          float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3])
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                       "f"(v[7])
+                       : "memory");
+          continue;
+        }
+        const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
+        if (p.flags & SMER_EPI_RELU) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
+        }
+        if (p.flags & SMER_EPI_GATE) {
+          float gte[8];
+          load8(rrow + col, gte);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
+        } else {
+          if (p.thr) {
+            float m0_[4], m1_[4];
+            const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
+            dropout4(seed, p.site, e4, p.thr, p.inv_keep, m0_);
+            dropout4(seed, p.site, e4 + 1, p.thr, p.inv_keep, m1_);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
+          }
+          if (rrow) {
+            float rs[8];
+            load8(rrow + col, rs);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] += rs[u];
+          }
+          if (p.flags & SMER_EPI_ACCUM) {
+            float old[8];
+            load8(crow + col, old);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] += old[u];
+          }
+        }
+        store8(crow + col, v);
       }
     }
   }
@@ -370,7 +393,7 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   p.C = C; p.ldc = ldc; p.bias = bias; p.resid = resid; p.ldr = ldr; p.M = M; p.N = N; p.flags = flags;
   p.thr = (dropout_p > 0.f && !(flags & SMER_EPI_GATE)) ? dropout_threshold(dropout_p) : 0u;
   p.inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-  p.seed = seed; p.site = site;
+  p.seed = seed; p.site = site; p.seed_dev = smer_seed_dev();
   p.num_kb = (K + BK - 1) / BK;
   if (split_k > p.num_kb) split_k = p.num_kb;
   p.kb_per_split = (p.num_kb + split_k - 1) / split_k;

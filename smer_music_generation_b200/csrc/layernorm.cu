@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ z_out, T* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, long long rows, int d, float eps, uint32_t thr, float inv_keep,
-              uint64_t seed, uint64_t site) {
+              uint64_t seed, uint64_t site, const unsigned long long* seed_dev) {
+  seed = eff_seed(seed, seed_dev);
   int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz,
               T* __restrict__ dbranch, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int d,
-              uint32_t thr, float inv_keep, uint64_t seed, uint64_t site) {
+              uint32_t thr, float inv_keep, uint64_t seed, uint64_t site, const unsigned long long* seed_dev) {
+  seed = eff_seed(seed, seed_dev);
   extern __shared__ float sm[];   // [2][warps][d]
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   long long warp = (long long)blockIdx.x * nw + wib;
@@ -186,7 +188,7 @@ static int ln_fwd_launch(const void* branch, const void* resid, const float* gam
 #define LN_CASE(I)                                                                                          \
   case I:                                                                                                   \
     ln_fwd_kernel<T, I><<<grid, 256, 0, st>>>((const T*)branch, (const T*)resid, gamma, beta, (T*)z, (T*)y, mean, \
-                                              rstd, rows, d, eps, thr, inv_keep, seed, site);              \
+                                              rstd, rows, d, eps, thr, inv_keep, seed, site, smer_seed_dev()); \
     break;
   switch (iters) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
@@ -229,7 +231,7 @@ static int ln_bwd_launch(const void* dy, const void* z, const float* mean, const
     if (smem > 48 * 1024)                                                                                       \
       cudaFuncSetAttribute(ln_bwd_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     ln_bwd_kernel<T, I><<<grid, 256, smem, st>>>((const T*)dy, (const T*)z, mean, rstd, gamma, (T*)dz, (T*)dbranch, \
-                                                 dgamma, dbeta, rows, d, thr, inv_keep, seed, site);            \
+                                                 dgamma, dbeta, rows, d, thr, inv_keep, seed, site, smer_seed_dev()); \
     break;
   switch (iters) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)

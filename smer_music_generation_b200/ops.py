@@ -222,10 +222,14 @@ def xent_bwd(logits, targets, W, lse, sums, dlogits, V, grad_scale=1.0, grad_sca
                                       _p(grad_scale_dev), K.stream()), "xent_bwd")
 
 
-def adam_step(p, g, m, v, shadow, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+def adam_step(p, g, m, v, shadow, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, step_dev=None):
     with _Timed("adam", float(p.numel() * (28 + (2 if shadow is not None else 0))), 1):
-        K.check(K.lib().smer_adam_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), step, lr, b1, b2, eps,
-                                       grad_scale, K.stream()), "adam_step")
+        if step_dev is not None:
+            K.check(K.lib().smer_adam_step_dev(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), _p(step_dev), lr, b1,
+                                               b2, eps, grad_scale, K.stream()), "adam_step_dev")
+        else:
+            K.check(K.lib().smer_adam_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), step, lr, b1, b2, eps,
+                                           grad_scale, K.stream()), "adam_step")
 
 
 def cast2d(src, dst, cols=None):

@@ -142,14 +142,18 @@ class TrainEngine:
     def step(self, src, tgt_in, tgt_out, src_pad=None, tgt_pad=None, update: bool = True):
         """All arguments are device tensors.  Returns the device tensor `sums` (fp64[16]):
         sums[0]/sums[1] is the loss, sums[2+k]/sums[1] the k-th category term."""
-        m = self.model
-        if not m.training:
+        if not self.model.training:
             raise RuntimeError("TrainEngine.step needs model.train()")
-        B, S = src.shape
-        T = tgt_in.shape[1]
         self.step_count += 1
         seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self.step_count * 0xD1342543DE82EF95
                 + (0 if self.pg is None else 7919 * torch.distributed.get_rank(self.pg))) & 0xFFFFFFFFFFFFFFFF
+        self._step_impl(src, tgt_in, tgt_out, src_pad, tgt_pad, seed, update, None)
+        return self.sums
+
+    def _step_impl(self, src, tgt_in, tgt_out, src_pad, tgt_pad, seed, update, step_dev):
+        m = self.model
+        B, S = src.shape
+        T = tgt_in.shape[1]
         pad_s = None if src_pad is None else src_pad.to(torch.uint8)
         pad_t = None if tgt_pad is None else tgt_pad.to(torch.uint8)
         run = _Run(m, src, tgt_in, pad_s, pad_t, pad_s, True, None, True, seed, False)
@@ -174,13 +178,61 @@ class TrainEngine:
         if self.buckets is not None:
             self.buckets.finish()
         if update:
-            self.adam()
+            a = self.arena
+            ops.adam_step(a.flat, self.grads.flat, a.m, a.v, a.shadow, self.step_count, self.lr, self.betas[0],
+                          self.betas[1], self.eps, 1.0, step_dev=step_dev)
+
+    # ---- the same step captured once into a CUDA graph ---------------------------------
+    def capture(self, B: int, S: int, T: int):
+        """Captures one full step (forward, loss, backward, Adam) for fixed shapes.  The dropout
+        seed and Adam's step number come from a device counter that the graph itself increments,
+        so every replay is a new training step.  Single-GPU only (collectives stay eager)."""
+        if self.world > 1:
+            raise RuntimeError("TrainEngine.capture: graph capture is single-GPU; use step() under DP")
+        dev = self.dev
+        self._g_in = dict(src=torch.zeros(B, S, dtype=torch.int64, device=dev),
+                          tgt_in=torch.zeros(B, T, dtype=torch.int64, device=dev),
+                          tgt_out=torch.zeros(B, T, dtype=torch.int64, device=dev),
+                          src_pad=torch.zeros(B, S, dtype=torch.bool, device=dev),
+                          tgt_pad=torch.zeros(B, T, dtype=torch.bool, device=dev))
+        gi = self._g_in
+        gi["src"].fill_(3); gi["tgt_in"].fill_(3); gi["tgt_out"].fill_(3)
+        self._ctr = torch.full((1,), self.step_count, dtype=torch.int64, device=dev)
+        K.check(K.lib().smer_set_seed_device_ptr(self._ctr.data_ptr()), "set_seed_device_ptr")
+        self._seed_base = (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        # warm-up outside capture (lazy kernel loads, cudaFuncSetAttribute), on a side stream
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._ctr.add_(1)
+            self.step_count += 1
+            self._step_impl(gi["src"], gi["tgt_in"], gi["tgt_out"], gi["src_pad"], gi["tgt_pad"], self._seed_base, True,
+                            self._ctr)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._ctr.add_(1)
+            self._step_impl(gi["src"], gi["tgt_in"], gi["tgt_out"], gi["src_pad"], gi["tgt_pad"], self._seed_base, True,
+                            self._ctr)
+        return self
+
+    def step_graph(self, src, tgt_in, tgt_out, src_pad, tgt_pad):
+        """Copies one batch (host pinned or device tensors) into the captured step's input buffers
+        and replays it.  Returns the device `sums` tensor."""
+        gi = self._g_in
+        gi["src"].copy_(src, non_blocking=True)
+        gi["tgt_in"].copy_(tgt_in, non_blocking=True)
+        gi["tgt_out"].copy_(tgt_out, non_blocking=True)
+        gi["src_pad"].copy_(src_pad, non_blocking=True)
+        gi["tgt_pad"].copy_(tgt_pad, non_blocking=True)
+        self.step_count += 1
+        self._graph.replay()
         return self.sums
 
-    def adam(self):
-        a = self.arena
-        ops.adam_step(a.flat, self.grads.flat, a.m, a.v, a.shadow, self.step_count, self.lr, self.betas[0],
-                      self.betas[1], self.eps, 1.0)
+    def release_graph(self):
+        self._graph = None
+        K.lib().smer_set_seed_device_ptr(None)
 
     def loss_value(self) -> float:
         s = self.sums.tolist()
