@@ -638,14 +638,25 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         ptx::tmem_ld_wait();
         float pd[32], ds[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const int col = c * 32 + k;
-          float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -s_lse[slot + col]));
-          if (key_masked || col < cm) pr = 0.f;
-          float keep = 1.f;
-          if (p.thr16) keep = ((attn_pair_bits(s_key[slot + col], j) >> jsh) & 0xFFFFu) >= p.thr16 ? p.inv_keep : 0.f;
-          pd[k] = pr * keep;
-          ds[k] = pr * (__uint_as_float(dv[k]) * keep - s_dsum[slot + col]);
+        for (int k4 = 0; k4 < 8; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
+          const int colb = c * 32 + k4 * 4;
+          const float4 l4 = *reinterpret_cast<const float4*>(s_lse + slot + colb);
+          const float4 d4 = *reinterpret_cast<const float4*>(s_dsum + slot + colb);
+          const uint4 key4 = *reinterpret_cast<const uint4*>(s_key + slot + colb);
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+          const uint32_t kk[4] = {key4.x, key4.y, key4.z, key4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = k4 * 4 + u;
+            const int col = colb + u;
+            float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lv[u]));
+            if (key_masked || col < cm) pr = 0.f;
+            float keep = 1.f;
+            if (p.thr16) keep = ((attn_pair_bits(kk[u], j) >> jsh) & 0xFFFFu) >= p.thr16 ? p.inv_keep : 0.f;
+            pd[k] = pr * keep;
+            ds[k] = pr * (__uint_as_float(dv[k]) * keep - dd[u]);
+          }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

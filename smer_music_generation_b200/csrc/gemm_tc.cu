@@ -6,7 +6,7 @@
 // (dX = dY.W uses B MN-major; dW = dY^T.X uses A and B MN-major with split-K fp32 atomics).
 //
 // Persistent: one CTA per SM walks a static list of (128x128 tile, K-split) work items, N fastest
-// so that concurrently running CTAs share A rows in L2.  K step 64, 4-stage smem ring (128 KB)
+// so that concurrently running CTAs share A rows in L2.  K step 64, 6-stage smem ring (192 KB)
 // that keeps filling across work items; TWO 128-column fp32 accumulators in TMEM so the epilogue
 // of item i overlaps the MMAs of item i+1.  Epilogue (8 warps): TMEM -> registers -> per-warp smem
 // transpose (so that one store instruction covers 4 full 128-byte row segments instead of 32
@@ -23,11 +23,11 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
 constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB per operand per stage
 constexpr int GEMM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
-constexpr int STAGE_EPI = 32 * 64 * 4;                        // per epilogue warp: 32 rows x 64 fp32 columns
+constexpr int STAGE_EPI = 32 * 32 * 4;                        // per epilogue warp: 32 rows x 32 fp32 columns (two rounds per item)
 constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + EPI_WARPS * STAGE_EPI + 1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -194,85 +194,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::tmem_ld_32x32(t_addr + 32, r1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      __syncwarp();                                            // also: previous item's staging reads are done
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);   // accumulator is in registers: MMA may reuse it
-      // stage: lane == tile row; 16-byte chunk c of the 256-byte row goes to chunk c ^ (row & 15)
-      {
-        const uint32_t rowbase = stage_addr + lane * 256;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(rowbase + (((uint32_t)c ^ (lane & 15)) << 4), r0[4 * c], r0[4 * c + 1], r0[4 * c + 2], r0[4 * c + 3]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(rowbase + (((uint32_t)(c + 8) ^ (lane & 15)) << 4), r1[4 * c], r1[4 * c + 1], r1[4 * c + 2], r1[4 * c + 3]);
-      }
       __syncwarp();
-      // drain: lane -> (row = it*4 + lane/8, 8 columns starting at (lane%8)*8): 4 rows x 128 B (bf16) per store
-      const int lc = (lane & 7) * 8;
-      const int col = n0 + chalf * 64 + lc;
-      if (col >= p.N) continue;                                // N % 8 == 0
-      float bias8[8];
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);   // accumulator is in registers: MMA may reuse it
+      // Two rounds of 32 columns: stage (lane == tile row; 16-byte chunk c of the 128-byte row goes to
+      // chunk c ^ (row & 7)), then drain with lane -> (row = it*8 + lane/4, 8 columns at (lane%4)*8):
+      // every store instruction covers 8 rows x 64 B (bf16) / 2 x 8 rows x 64 B (fp32).
+      const int lc = (lane & 3) * 8;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) bias8[u] = 0.f;
-      if (p.bias && (!(p.flags & SMER_EPI_ATOMIC) || sp == 0)) load8(p.bias + col, bias8);
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int rl = it * 4 + (lane >> 3);
-        const int row = m0 + quarter * 32 + rl;
-        if (row >= p.M) continue;
-        float v[8];
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t* r = hh == 0 ? r0 : r1;
+        __syncwarp();                                          // previous round's staging reads are done
         {
-          const uint32_t rowbase = stage_addr + rl * 256;
-          const uint32_t c0 = (uint32_t)(lc >> 2);
-          ld_shared_v4(rowbase + ((c0 ^ (rl & 15)) << 4), v);
-          ld_shared_v4(rowbase + (((c0 + 1) ^ (rl & 15)) << 4), v + 4);
+          const uint32_t rowbase = stage_addr + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            st_shared_v4(rowbase + (((uint32_t)c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         }
+        __syncwarp();
+        const int col = n0 + chalf * 64 + hh * 32 + lc;
+        if (col >= p.N) continue;                              // N % 8 == 0
+        float bias8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] += bias8[u];
-        TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
-        if (p.flags & SMER_EPI_ATOMIC) {
-          float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                       "f"(v[3])
-                       : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
-                       "f"(v[7])
-                       : "memory");
-          continue;
-        }
-        const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
-        if (p.flags & SMER_EPI_RELU) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
-        }
-        if (p.flags & SMER_EPI_GATE) {
-          float gte[8];
-          load8(rrow + col, gte);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
-        } else {
-          if (p.thr) {
-            float m0_[4], m1_[4];
-            const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
-            dropout4(seed, p.site, e4, p.thr, p.inv_keep, m0_);
-            dropout4(seed, p.site, e4 + 1, p.thr, p.inv_keep, m1_);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
+        for (int u = 0; u < 8; ++u) bias8[u] = 0.f;
+        if (p.bias && (!(p.flags & SMER_EPI_ATOMIC) || sp == 0)) load8(p.bias + col, bias8);
+#pragma unroll 2
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 8 + (lane >> 2);
+          const int row = m0 + quarter * 32 + rl;
+          if (row >= p.M) continue;
+          float v[8];
+          {
+            const uint32_t rowbase = stage_addr + rl * 128;
+            const uint32_t c0 = (uint32_t)(lc >> 2);
+            ld_shared_v4(rowbase + ((c0 ^ (rl & 7)) << 4), v);
+            ld_shared_v4(rowbase + (((c0 + 1) ^ (rl & 7)) << 4), v + 4);
           }
-          if (rrow) {
-            float rs[8];
-            load8(rrow + col, rs);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += rs[u];
+          for (int u = 0; u < 8; ++u) v[u] += bias8[u];
+          TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
+          if (p.flags & SMER_EPI_ATOMIC) {
+            float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                         "f"(v[3])
+                         : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                         "f"(v[7])
+                         : "memory");
+            continue;
           }
-          if (p.flags & SMER_EPI_ACCUM) {
-            float old[8];
-            load8(crow + col, old);
+          const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
+          if (p.flags & SMER_EPI_RELU) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] += old[u];
+            for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
           }
+          if (p.flags & SMER_EPI_GATE) {
+            float gte[8];
+            load8(rrow + col, gte);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
+          } else {
+            if (p.thr) {
+              float m0_[4], m1_[4];
+              const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
+              dropout4(seed, p.site, e4, p.thr, p.inv_keep, m0_);
+              dropout4(seed, p.site, e4 + 1, p.thr, p.inv_keep, m1_);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
+            }
+            if (rrow) {
+              float rs[8];
+              load8(rrow + col, rs);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] += rs[u];
+            }
+            if (p.flags & SMER_EPI_ACCUM) {
+              float old[8];
+              load8(crow + col, old);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] += old[u];
+            }
+          }
+          store8(crow + col, v);
         }
-        store8(crow + col, v);
       }
     }
   }
