@@ -524,7 +524,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *sp_full = bars + 5,
            *pds_full = bars + 6, *done = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  float* s_lse = reinterpret_cast<float*>(tmem_ptr + 2);      // [2][64]
+  float* s_lse = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);      // [2][64], 16-byte aligned
   float* s_dsum = s_lse + 2 * BKV;                            // [2][64]
   uint32_t* s_key = reinterpret_cast<uint32_t*>(s_dsum + 2 * BKV);   // [2][64]
 
