@@ -22,6 +22,20 @@ __device__ __forceinline__ void load_row(const T* p, float (&v)[EPL]) {
     v[c] = t[0]; v[c + 1] = t[1]; v[c + 2] = t[2]; v[c + 3] = t[3];
   }
 }
+// 8 bf16 = one 16-byte streaming load (the K/V caches are read once per step: do not allocate in L1)
+template <>
+__device__ __forceinline__ void load_row<bf16, 8>(const bf16* p, float (&v)[8]) {
+  uint4 t;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
 template <typename T, int DH>
 __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(smer_decode_attn_args a) {
   constexpr int EPL = DH >= 64 ? 8 : 4;          // elements per lane
@@ -64,29 +78,39 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(smer_decode_at
 #pragma unroll
   for (int c = 0; c < EPL; ++c) acc[c] = 0.f;
   const uint8_t* pad = a.key_pad ? a.key_pad + (long long)s * a.ld_pad : nullptr;
-#pragma unroll 2
-  for (int jb = j0; jb < j1; jb += DEC_GROUPS) {    // trip count is uniform across the CTA
-    int j = jb + grp;
-    bool valid = j < j1;
-    int jc = valid ? j : j1 - 1;
-    float kr[EPL], vr[EPL];
-    bool fresh = nk && jc == npast;
-    const T* kp = fresh ? nk : kc + (long long)jc * a.ld_cache;
-    const T* vp = fresh ? nv : vc + (long long)jc * a.ld_cache;
-    load_row<T, EPL>(kp, kr);
-    load_row<T, EPL>(vp, vr);
-    float d = 0.f;
+  // HBM-bound loop: every thread first issues the K and V loads of U key rows (2*U independent
+  // 16-byte requests in flight), then folds them into its online softmax.
+  constexpr int U = 4;
+  for (int jb = j0; jb < j1; jb += DEC_GROUPS * U) {    // trip count is uniform across the CTA
+    float kr[U][EPL], vr[U][EPL];
+    bool valid[U];
 #pragma unroll
-    for (int c = 0; c < EPL; ++c) d = fmaf(qr[c], kr[c], d);
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u * DEC_GROUPS + grp;
+      valid[u] = j < j1;
+      const int jc = valid[u] ? j : j1 - 1;
+      const bool fresh = nk && jc == npast;
+      const T* kp = fresh ? nk : kc + (long long)jc * a.ld_cache;
+      const T* vp = fresh ? nv : vc + (long long)jc * a.ld_cache;
+      load_row<T, EPL>(kp, kr[u]);
+      load_row<T, EPL>(vp, vr[u]);
+      if (pad && valid[u] && pad[jc]) valid[u] = false;
+    }
 #pragma unroll
-    for (int o = 1; o < LPK; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (valid && !(pad && pad[jc])) {
-      float mn = fmaxf(m, d);
-      float alpha = expf(m - mn), pr = expf(d - mn);
-      l = l * alpha + pr;
+    for (int u = 0; u < U; ++u) {
+      float d = 0.f;
 #pragma unroll
-      for (int c = 0; c < EPL; ++c) acc[c] = fmaf(pr, vr[c], acc[c] * alpha);
-      m = mn;
+      for (int c = 0; c < EPL; ++c) d = fmaf(qr[c], kr[u][c], d);
+#pragma unroll
+      for (int o = 1; o < LPK; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (valid[u]) {
+        float mn = fmaxf(m, d);
+        float alpha = __expf(m - mn), pr = __expf(d - mn);
+        l = l * alpha + pr;
+#pragma unroll
+        for (int c = 0; c < EPL; ++c) acc[c] = fmaf(pr, vr[u][c], acc[c] * alpha);
+        m = mn;
+      }
     }
   }
   if (lig == 0) { sm_m[grp] = m; sm_l[grp] = l; }

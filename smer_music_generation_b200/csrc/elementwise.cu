@@ -159,45 +159,96 @@ extern "C" int smer_cast_f32_to_bf16(const float* src, void* dst, long long n, v
 }
 
 // ---------------------------------------------------------------------------------------
-// bias gradient: out[c] (+)= sum_r x[r, c].   Block = 32x8 threads; each block owns a 32-column
-// strip and a slab of rows, reduces in shared memory and issues one atomic per column.
+// bias gradient: out[c] += sum_r x[r, c].  Block = 32 column-groups x 8 row-lanes; each thread
+// owns 8 consecutive columns (one 16-byte load per row for bf16, two for fp32) and strides over
+// a slab of rows with 4 loads in flight, then the 8 row-lanes are reduced through shared memory
+// and one atomic per column per block is issued.
 // ---------------------------------------------------------------------------------------
-template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, long long rows,
-                              int cols, long long rows_per_block) {
-  __shared__ float sm[8][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int cols,
+              long long rows_per_block) {
+  __shared__ float sm[8][32 * 8 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + cg) * 8;
   long long r0 = (long long)blockIdx.y * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
-  float acc = 0.f;
-  if (c < cols)
-    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f32(x[r * ld + c]);
-  sm[threadIdx.y][threadIdx.x] = acc;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (c0 < cols) {
+    if (VEC) {
+      long long r = r0 + rl;
+      for (; r + 24 < r1; r += 32) {                 // 4 independent 16-byte loads in flight
+        float v0[8], v1[8], v2[8], v3[8];
+        ld8(x + r * ld + c0, v0);
+        ld8(x + (r + 8) * ld + c0, v1);
+        ld8(x + (r + 16) * ld + c0, v2);
+        ld8(x + (r + 24) * ld + c0, v3);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+      }
+      for (; r < r1; r += 8) {
+        float v0[8];
+        ld8(x + r * ld + c0, v0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v0[k];
+      }
+    } else {
+      for (long long r = r0 + rl; r < r1; r += 8)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k < cols) acc[k] += to_f32(x[r * ld + c0 + k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sm[rl][cg * 8 + k] = acc[k];
   __syncthreads();
-  if (threadIdx.y == 0 && c < cols) {
+  const int c = threadIdx.x;                       // 256 columns per block
+  const int gc = blockIdx.x * 256 + c;
+  if (gc < cols) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += sm[k][threadIdx.x];
-    atomicAdd(out + c, s);
+    for (int k = 0; k < 8; ++k) s += sm[k][c];
+    atomicAdd(out + gc, s);
   }
 }
 
 extern "C" int smer_colsum(const void* x, int dtype, long long ld, float* out, long long rows, int cols,
                            void* stream) {
   if (rows == 0 || cols == 0) return SMER_OK;
-  int gx = (cols + 31) / 32;
+  int gx = (cols + 255) / 256;
   long long target = (long long)smer_num_sms() * 8 / gx;
   if (target < 1) target = 1;
   long long rpb = (rows + target - 1) / target;
   if (rpb < 64) rpb = 64;
   int gy = (int)((rows + rpb - 1) / rpb);
-  dim3 grid(gx, gy), block(32, 8);
+  dim3 grid(gx, gy);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SMER_DT_F32)
-    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, out, rows, cols, rpb);
-  else
-    colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, ld, out, rows, cols, rpb);
+  const bool vec = cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (dtype == SMER_DT_F32) {
+    if (vec) colsum_kernel<float, true><<<grid, 256, 0, st>>>((const float*)x, ld, out, rows, cols, rpb);
+    else colsum_kernel<float, false><<<grid, 256, 0, st>>>((const float*)x, ld, out, rows, cols, rpb);
+  } else {
+    if (vec) colsum_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)x, ld, out, rows, cols, rpb);
+    else colsum_kernel<bf16, false><<<grid, 256, 0, st>>>((const bf16*)x, ld, out, rows, cols, rpb);
+  }
   SMER_CHECK_LAUNCH("smer_colsum");
   return SMER_OK;
 }

@@ -71,11 +71,35 @@ __device__ __forceinline__ double uniform01(uint64_t seed, uint64_t seq, uint64_
   return ((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// In-place inclusive prefix sum of x[0..VMAX) by warp 0: each lane sums a block of VMAX/32 entries,
+// the block totals are scanned with shuffles, then the prefixes are written back.
+__device__ __forceinline__ void warp0_inclusive_scan(double* x, int tid) {
+  if (tid >= 32) return;
+  constexpr int PER = VMAX / 32;
+  double loc[PER];
+  double run = 0.0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    run += x[tid * PER + k];
+    loc[k] = run;
+  }
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (tid >= o) incl += up;
+  }
+  const double base = incl - run;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) x[tid * PER + k] = base + loc[k];
+}
+
 __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
   __shared__ double q[VMAX];
   __shared__ double red[128];
   __shared__ int order[VMAX];
-  __shared__ int chosen;
+  __shared__ double cdf[VMAX];
+  __shared__ int chosen, shared_keep;
   int s = blockIdx.x;
   int tid = threadIdx.x;
   if (a.done && a.done[s]) return;
@@ -146,45 +170,70 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
       order[rank] = i;
     }
     __syncthreads();
-    if (tid == 0) {
-      int keep = V;
-      if (a.mode == SMER_SAMPLE_TOP_P) {
-        double cs = 0.0;
-        for (int r = 0; r < V; ++r) {
-          cs += q[order[r]];
-          if (cs > a.top_p) { keep = r + 1; break; }
-        }
-      } else {
-        keep = a.top_k < 1 ? 1 : (a.top_k > V ? V : a.top_k);
-      }
-      double ks = 0.0;
-      for (int r = 0; r < keep; ++r) ks += q[order[r]];
-      for (int r = 0; r < V; ++r) {
-        int i = order[r];
-        q[i] = r < keep ? q[i] / ks : 0.0;
-      }
+    // cumulative probability in rank order (warp 0 scans), then the cut-off and renormalisation
+    for (int r = tid; r < VMAX; r += 128) cdf[r] = r < V ? q[order[r]] : 0.0;
+    __syncthreads();
+    warp0_inclusive_scan(cdf, tid);
+    __syncthreads();
+    int keep;
+    if (a.mode == SMER_SAMPLE_TOP_P) {
+      // first rank whose cumulative sum exceeds p, inclusive (generation.py:17-22)
+      if (tid == 0) shared_keep = V;
+      __syncthreads();
+      for (int r = tid; r < V; r += 128)
+        if (cdf[r] > a.top_p && (r == 0 || !(cdf[r - 1] > a.top_p))) shared_keep = r + 1;
+      __syncthreads();
+      keep = shared_keep;
+    } else {
+      keep = a.top_k < 1 ? 1 : (a.top_k > V ? V : a.top_k);
+    }
+    const double ks = cdf[keep - 1];
+    __syncthreads();
+    for (int r = tid; r < V; r += 128) {
+      const int i = order[r];
+      q[i] = r < keep ? q[i] / ks : 0.0;
     }
     __syncthreads();
   }
   if (a.out_probs)
     for (int i = tid; i < V; i += 128) a.out_probs[(long long)s * V + i] = q[i];
 
+  if (a.mode == SMER_SAMPLE_GREEDY) {
+    // argmax, lowest id on ties
+    double best = -1.0;
+    int bi = 0;
+    for (int i = tid; i < V; i += 128)
+      if (q[i] > best) { best = q[i]; bi = i; }
+    red[tid] = best;
+    order[tid] = bi;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (tid < o && (red[tid + o] > red[tid] || (red[tid + o] == red[tid] && order[tid + o] < order[tid]))) {
+        red[tid] = red[tid + o];
+        order[tid] = order[tid + o];
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int i = tid; i < VMAX; i += 128) cdf[i] = i < V ? q[i] : 0.0;
+    __syncthreads();
+    warp0_inclusive_scan(cdf, tid);
+    __syncthreads();
+  }
   if (tid == 0) {
     int idx = 0;
     if (a.mode == SMER_SAMPLE_GREEDY) {
-      double best = -1.0;
-      for (int i = 0; i < V; ++i)
-        if (q[i] > best) { best = q[i]; idx = i; }
+      idx = order[0];
     } else {
       uint64_t step = a.step_base + (a.gen_count ? (uint64_t)a.gen_count[s] : 0);
       for (uint32_t draw = 0; draw < 12; ++draw) {
         double u = uniform01(a.seed, (uint64_t)(a.seq_base + s), step, draw);
-        double cs = 0.0;
-        idx = V - 1;
-        for (int i = 0; i < V; ++i) {
-          cs += q[i];
-          if (u < cs) { idx = i; break; }
+        int lo = 0, hi = V - 1;                  // first i with u < cdf[i]  (cdf is non-decreasing)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (u < cdf[mid]) hi = mid; else lo = mid + 1;
         }
+        idx = lo;
         if (a.raw_flags || accepted(f.accept, idx)) break;     // draws 0..10 must be accepted, draw 11 is kept
       }
     }
