@@ -7,10 +7,12 @@
 //   warp 0      TMA producer: Q once, then K_t / V_t into single smem slots (K's slot is free as
 //               soon as S_t = Q K_t^T has been read by the tensor core, V's after O_t = P_t V_t)
 //   warp 1      tcgen05.mma issuer (one elected thread) + TMEM owner (256 columns: S 128, O_t 64)
-//   warps 2..5  softmax: thread <-> TMEM lane <-> query row.  Two passes over S in TMEM (max, then
-//               exp2 / row-sum / dropout / bf16 pack), P written to smem in the SWIZZLE_128B
-//               K-major layout the PV MMA reads; O accumulated in fp32 registers with the
-//               online-softmax rescale after each PV tile.
+//   warps 2..9  softmax: TWO threads per query row (TMEM lane), each owning 64 of the tile's 128
+//               keys and 32 of the 64 output columns -- 8 warps per CTA are what keeps the SM's
+//               issue slots busy (ncu: with 4 the kernel was latency-bound at 52 % issue).  Two
+//               passes over S in TMEM (max -> exchanged through smem, then exp2 / row-sum / dropout
+//               / bf16 pack), P written to smem in the SWIZZLE_128B K-major layout the PV MMA
+//               reads; O accumulated in fp32 registers with the online-softmax rescale.
 //   Two CTAs share an SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
 //   other's MMAs.
 #include "common.cuh"
@@ -25,8 +27,8 @@ namespace {
 constexpr int BM = 128, BN = 128, DH = 64;
 constexpr int TILE_QKV = BM * DH * 2;            // 16 KB
 constexpr int TILE_P = BM * BN * 2;              // 32 KB (two 64-key halves of 16 KB)
-constexpr int FWD_THREADS = 192;
-constexpr int FWD_SMEM = 3 * TILE_QKV + TILE_P + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int FWD_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
+constexpr int FWD_SMEM = 3 * TILE_QKV + TILE_P + 1024 /*align*/ + 2560 /*barriers + row exchange*/;
 constexpr int TMEM_COLS = 256;
 constexpr int O_COL = 128;
 
@@ -53,7 +55,13 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 8 consecutive bf16 of a row (16-byte chunk c16 of a 128-byte SWIZZLE_128B row)
+__device__ __forceinline__ void st_row_chunk_fwd(uint32_t row_addr, uint32_t rx, uint32_t c16, const float* v) {
+  st_shared_v4(row_addr + ((c16 ^ rx) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+               pack_bf16x2(v[6], v[7]));
+}
 __device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_bwd() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -69,6 +77,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
            *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
   uint32_t* padw = tmem_ptr + 2;                 // [2][4] mask words of the current KV tile
+  float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 parity][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;     // heavy (late-causal) query tiles first
@@ -82,7 +91,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 128 : 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 256 : 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -138,47 +147,50 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;              // keys [hf*64, hf*64+64) of every tile, output columns [hf*32, hf*32+32)
     const int r = quarter * 32 + lane;
     const int i = i0 + r;
     const bool row_ok = i < p.Lq;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t sP_row = ptx::smem_u32(sP) + r * 128;
+    const uint32_t sP_row = ptx::smem_u32(sP) + hf * (TILE_P / 2) + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
     const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
     const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
     const float c2 = p.c_log2;
-    float m = -INFINITY, l = 0.f;
-    float acc[DH];
+    float m = -INFINITY, l = 0.f;               // l: this thread's half of the row sum
+    float acc[32];
 #pragma unroll
-    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
 
     for (int t = 0; t < ntiles; ++t) {
       const int j0 = t * BN;
-      uint32_t mw[4] = {0u, 0u, 0u, 0u};
+      uint32_t mw[2] = {0u, 0u};
       if (p.pad != nullptr || j0 + BN > kend) {
-        const int j = j0 + r;
-        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
-        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
-        if (lane == 0) padw[(t & 1) * 4 + quarter] = bal;
-        bar_sync_softmax();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) mw[c] = padw[(t & 1) * 4 + c];
+        if (hf == 0) {
+          const int j = j0 + r;
+          const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
+          const uint32_t bal = __ballot_sync(0xffffffffu, msk);
+          if (lane == 0) padw[(t & 1) * 4 + quarter] = bal;
+        }
+        bar_sync_bwd();
+        mw[0] = padw[(t & 1) * 4 + hf * 2];
+        mw[1] = padw[(t & 1) * 4 + hf * 2 + 1];
       }
       if (p.causal && j0 + BN - 1 > i0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int nvis = i - (j0 + c * 32) + 1;
+        for (int c = 0; c < 2; ++c) {
+          const int nvis = i - (j0 + hf * 64 + c * 32) + 1;
           mw[c] |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
         }
       }
       ptx::mbar_wait(s_full, t & 1);
       ptx::tc_fence_after();
-      // ---- pass 1: row maximum of the visible scores
+      // ---- pass 1: maximum of this thread's 64 visible scores, then the row maximum via smem
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32(lane_addr + c * 32, v);
+        ptx::tmem_ld_32x32(lane_addr + hf * 64 + c * 32, v);
         ptx::tmem_ld_wait();
         const uint32_t w = mw[c];
         if (w == 0u) {
@@ -189,64 +201,66 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int k = 0; k < 32; ++k) mx = fmaxf(mx, ((w >> k) & 1u) ? -INFINITY : __uint_as_float(v[k]));
         }
       }
+      float* xch = s_xch + (t & 1) * 256;
+      xch[hf * 128 + r] = mx;
+      bar_sync_bwd();
+      mx = fmaxf(mx, xch[(hf ^ 1) * 128 + r]);
       const float m_new = fmaxf(m, mx * c2);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2(m - m_use);
       float lsum = 0.f;
       // ---- pass 2: P = exp2(S*c - m), row sum, dropout, bf16 pack into the swizzled A-operand tile
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(lane_addr + c * 32, v);
+      for (int sc = 0; sc < 4; ++sc) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(lane_addr + hf * 64 + sc * 16, v);
         ptx::tmem_ld_wait();
-        const uint32_t w = mw[c];
-        float pv[32];
+        const uint32_t w = mw[sc >> 1] >> ((sc & 1) * 16);
+        float pv[16];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float s = __uint_as_float(v[k]);
-          if (w != 0u) s = ((w >> k) & 1u) ? -INFINITY : s;
-          pv[k] = ex2(fmaf(s, c2, -m_use));
+        for (int k = 0; k < 16; ++k) {
+          float sval = __uint_as_float(v[k]);
+          if ((w & 0xFFFFu) != 0u) sval = ((w >> k) & 1u) ? -INFINITY : sval;
+          pv[k] = ex2(fmaf(sval, c2, -m_use));
           lsum += pv[k];
         }
         if (p.thr16) {
 #pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2) {
-            const uint32_t bits = attn_pair_bits(rowkey, j0 + c * 32 + 2 * k2);
+          for (int k2 = 0; k2 < 8; ++k2) {
+            const uint32_t bits = attn_pair_bits(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2);
             pv[2 * k2] = (bits & 0xFFFFu) >= p.thr16 ? pv[2 * k2] * p.inv_keep : 0.f;
             pv[2 * k2 + 1] = (bits >> 16) >= p.thr16 ? pv[2 * k2 + 1] * p.inv_keep : 0.f;
           }
         }
-        const uint32_t half_base = sP_row + (c >> 1) * (TILE_P / 2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t c16 = (uint32_t)((c & 1) * 4 + q);
-          st_shared_v4(half_base + ((c16 ^ rx) << 4), pack_bf16x2(pv[8 * q], pv[8 * q + 1]),
-                       pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]), pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]),
-                       pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
-        }
+        for (int q = 0; q < 2; ++q) st_row_chunk_fwd(sP_row, rx, (uint32_t)(sc * 2 + q), pv + 8 * q);
       }
       l = l * alpha + lsum;
       m = m_new;
       ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core
       ptx::tc_fence_before();            // orders this thread's tcgen05.ld before the next MMAs
       ptx::mbar_arrive(p_full);
-      // ---- O += P V  (rescale the running accumulator, add the tile result)
+      // ---- O += P V  (rescale the running accumulator, add the tile result): this thread's 32 columns
       ptx::mbar_wait(o_full, t & 1);
       ptx::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t v[32];
-        ptx::tmem_ld_32x32(lane_addr + O_COL + c * 32, v);
+        ptx::tmem_ld_32x32(lane_addr + O_COL + hf * 32, v);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc[c * 32 + k] = fmaf(acc[c * 32 + k], alpha, __uint_as_float(v[k]));
+        for (int k = 0; k < 32; ++k) acc[k] = fmaf(acc[k], alpha, __uint_as_float(v[k]));
       }
     }
+    // row sum = both halves
+    float* xch = s_xch + (ntiles & 1) * 256;
+    xch[hf * 128 + r] = l;
+    bar_sync_bwd();
+    l += xch[(hf ^ 1) * 128 + r];
     if (row_ok) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      bf16* orow = p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH;
+      bf16* orow = p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH + hf * 32;
 #pragma unroll
-      for (int c = 0; c < DH; c += 8) {
+      for (int c = 0; c < 32; c += 8) {
         uint4 u;
         u.x = pack_bf16x2(acc[c] * inv, acc[c + 1] * inv);
         u.y = pack_bf16x2(acc[c + 2] * inv, acc[c + 3] * inv);
@@ -254,7 +268,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         u.w = pack_bf16x2(acc[c + 6] * inv, acc[c + 7] * inv);
         *reinterpret_cast<uint4*>(orow + c) = u;
       }
-      if (p.lse) p.lse[((long long)b * p.H + h) * p.Lq + i] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      if (p.lse && hf == 0)
+        p.lse[((long long)b * p.H + h) * p.Lq + i] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
     }
   }
   ptx::tc_fence_before();
@@ -275,7 +290,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // =========================================================================================
 constexpr int BKV = 64;                         // second tile dimension of both backward kernels
 constexpr int TILE_HALF = BKV * DH * 2;         // 8 KB
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps (2 threads per TMEM lane)
 constexpr int DQ_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + TILE_QKV + 1024 + 256;
 constexpr int DKV_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + 2 * TILE_QKV + 1024 + 2048;
 
@@ -357,7 +372,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 128 : 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 256 : 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -413,6 +428,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;                    // this thread's 32 of the tile's 64 key columns / dQ columns
     const int r = quarter * 32 + lane;
     const int i = i0 + r;
     const bool row_ok = i < p.Lq;
@@ -436,7 +452,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
         const uint32_t bal = __ballot_sync(0xffffffffu, msk);
         if (lane == 0) padw[(t & 1) * 2 + (quarter & 1)] = bal;       // quarters 0/2 and 1/3 write equal words
-        bar_sync_softmax();
+        bar_sync_bwd();
         mw[0] = padw[(t & 1) * 2];
         mw[1] = padw[(t & 1) * 2 + 1];
       }
@@ -449,27 +465,30 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       ptx::mbar_wait(sp_full, t & 1);
       ptx::tc_fence_after();
+      {
+        const uint32_t w = mw[hf];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        ptx::tmem_ld_32x32(lane_addr + c * 32, sv);
-        ptx::tmem_ld_32x32(lane_addr + 64 + c * 32, dv);
-        ptx::tmem_ld_wait();
-        const uint32_t w = mw[c];
-        float ds[32];
+        for (int sc = 0; sc < 2; ++sc) {               // two 16-column sub-chunks keep the register count low
+          const int cb = hf * 32 + sc * 16;
+          uint32_t sv[16], dv[16];
+          ptx::tmem_ld_32x16(lane_addr + cb, sv);
+          ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
+          ptx::tmem_ld_wait();
+          float ds[16];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lse2));
-          if (w != 0u) pr = ((w >> k) & 1u) ? 0.f : pr;
-          float dp = __uint_as_float(dv[k]);
-          if (p.thr16) {
-            const uint32_t bits = attn_pair_bits(rowkey, j0 + c * 32 + k);
-            dp = ((bits >> ((k & 1) * 16)) & 0xFFFFu) >= p.thr16 ? dp * p.inv_keep : 0.f;
+          for (int k = 0; k < 16; ++k) {
+            float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lse2));
+            if (w != 0u) pr = ((w >> (sc * 16 + k)) & 1u) ? 0.f : pr;
+            float dp = __uint_as_float(dv[k]);
+            if (p.thr16) {
+              const uint32_t bits = attn_pair_bits(rowkey, j0 + cb + k);
+              dp = ((bits >> ((k & 1) * 16)) & 0xFFFFu) >= p.thr16 ? dp * p.inv_keep : 0.f;
+            }
+            ds[k] = pr * (dp - dsum);
           }
-          ds[k] = pr * (dp - dsum);
-        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) st_row_chunk(row_addr, rx, (uint32_t)(c * 4 + q), ds + 8 * q);
+          for (int q = 0; q < 2; ++q) st_row_chunk(row_addr, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
+        }
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
@@ -479,12 +498,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::mbar_wait(dq_done, 0);
       ptx::tc_fence_after();
     }
-    bf16* drow = p.dq + ((long long)b * p.Lq + i) * p.lddq + h * DH;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    bf16* drow = p.dq + ((long long)b * p.Lq + i) * p.lddq + h * DH + hf * 32;
+    {
       uint32_t v[32];
       if (ntiles > 0) {                    // warp-uniform: tcgen05.ld is .sync.aligned
-        ptx::tmem_ld_32x32(lane_addr + 128 + c * 32, v);
+        ptx::tmem_ld_32x32(lane_addr + 128 + hf * 32, v);
         ptx::tmem_ld_wait();
       } else {
 #pragma unroll
@@ -498,7 +516,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           u.y = pack_bf16x2(__uint_as_float(v[k + 2]) * p.scale, __uint_as_float(v[k + 3]) * p.scale);
           u.z = pack_bf16x2(__uint_as_float(v[k + 4]) * p.scale, __uint_as_float(v[k + 5]) * p.scale);
           u.w = pack_bf16x2(__uint_as_float(v[k + 6]) * p.scale, __uint_as_float(v[k + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(drow + c * 32 + k) = u;
+          *reinterpret_cast<uint4*>(drow + k) = u;
         }
       }
     }
@@ -538,7 +556,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 128 : 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 256 : 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -598,6 +616,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncwarp();
   } else {
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;                    // this thread's 32 of the tile's 64 query columns / output columns
     const int r = quarter * 32 + lane;
     const int j = j0 + r;
     const bool row_ok = j < p.Lk;
@@ -612,7 +631,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int n = 0; n < ntiles; ++n) {
       const int iq0 = (it0 + n) * BKV;
       const int slot = (n & 1) * BKV;
-      if (r < BKV) {
+      if (r < BKV && hf == 0) {
         const int i = iq0 + r;
         float l2 = INFINITY, ds_ = 0.f;
         uint32_t rk = 0u;
@@ -626,20 +645,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         s_dsum[slot + r] = ds_;
         s_key[slot + r] = rk;
       }
-      bar_sync_softmax();
+      bar_sync_bwd();
       const int cm = (p.causal && iq0 < j0 + BM) ? (j - iq0) : 0;       // query columns < cm cannot see key j
       ptx::mbar_wait(sp_full, n & 1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        ptx::tmem_ld_32x32(lane_addr + c * 32, sv);
-        ptx::tmem_ld_32x32(lane_addr + 64 + c * 32, dv);
+      for (int sc = 0; sc < 2; ++sc) {
+        const int cb = hf * 32 + sc * 16;
+        uint32_t sv[16], dv[16];
+        ptx::tmem_ld_32x16(lane_addr + cb, sv);
+        ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
         ptx::tmem_ld_wait();
-        float pd[32], ds[32];
+        float pd[16], ds[16];
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
-          const int colb = c * 32 + k4 * 4;
+        for (int k4 = 0; k4 < 4; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
+          const int colb = cb + k4 * 4;
           const float4 l4 = *reinterpret_cast<const float4*>(s_lse + slot + colb);
           const float4 d4 = *reinterpret_cast<const float4*>(s_dsum + slot + colb);
           const uint4 key4 = *reinterpret_cast<const uint4*>(s_key + slot + colb);
@@ -659,9 +679,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          st_row_chunk(pd_row, rx, (uint32_t)(c * 4 + q), pd + 8 * q);
-          st_row_chunk(ds_row, rx, (uint32_t)(c * 4 + q), ds + 8 * q);
+        for (int q = 0; q < 2; ++q) {
+          st_row_chunk(pd_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), pd + 8 * q);
+          st_row_chunk(ds_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
         }
       }
       ptx::fence_proxy_async();
@@ -673,29 +693,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       ptx::tc_fence_after();
     }
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {           // 0: dK (scaled), 1: dV
-      bf16* drow = (part == 0 ? p.dk + ((long long)b * p.Lk + j) * p.lddk : p.dv + ((long long)b * p.Lk + j) * p.lddv) + h * DH;
+    for (int part = 0; part < 2; ++part) {           // 0: dK (scaled), 1: dV; this thread's 32 columns
+      bf16* drow = (part == 0 ? p.dk + ((long long)b * p.Lk + j) * p.lddk : p.dv + ((long long)b * p.Lk + j) * p.lddv) + h * DH + hf * 32;
       const float sc = part == 0 ? p.scale : 1.f;
+      uint32_t v[32];
+      if (ntiles > 0) {
+        ptx::tmem_ld_32x32(lane_addr + 128 + part * 64 + hf * 32, v);
+        ptx::tmem_ld_wait();
+      } else {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        if (ntiles > 0) {
-          ptx::tmem_ld_32x32(lane_addr + 128 + part * 64 + c * 32, v);
-          ptx::tmem_ld_wait();
-        } else {
+        for (int k = 0; k < 32; ++k) v[k] = 0u;
+      }
+      if (row_ok) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) v[k] = 0u;
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int k = 0; k < 32; k += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[k]) * sc, __uint_as_float(v[k + 1]) * sc);
-            u.y = pack_bf16x2(__uint_as_float(v[k + 2]) * sc, __uint_as_float(v[k + 3]) * sc);
-            u.z = pack_bf16x2(__uint_as_float(v[k + 4]) * sc, __uint_as_float(v[k + 5]) * sc);
-            u.w = pack_bf16x2(__uint_as_float(v[k + 6]) * sc, __uint_as_float(v[k + 7]) * sc);
-            *reinterpret_cast<uint4*>(drow + c * 32 + k) = u;
-          }
+        for (int k = 0; k < 32; k += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[k]) * sc, __uint_as_float(v[k + 1]) * sc);
+          u.y = pack_bf16x2(__uint_as_float(v[k + 2]) * sc, __uint_as_float(v[k + 3]) * sc);
+          u.z = pack_bf16x2(__uint_as_float(v[k + 4]) * sc, __uint_as_float(v[k + 5]) * sc);
+          u.w = pack_bf16x2(__uint_as_float(v[k + 6]) * sc, __uint_as_float(v[k + 7]) * sc);
+          *reinterpret_cast<uint4*>(drow + k) = u;
         }
       }
     }

@@ -8,7 +8,52 @@
 
 constexpr int LN_MAX_ITERS = 8;   // d <= 8 * 128 = 1024
 
-template <typename T, int ITERS>
+// VEC consecutive elements per lane per iteration: 4 for fp32 (16-byte accesses), 8 for bf16 (16 bytes)
+template <int VEC> struct VecIO;
+template <> struct VecIO<4> {
+  template <typename T> static __device__ __forceinline__ void ld(const T* p, float (&v)[4]) { load4(p, v); }
+  template <typename T> static __device__ __forceinline__ void st(T* p, const float (&v)[4]) { store4(p, v); }
+  static __device__ __forceinline__ void drop(uint64_t seed, uint64_t site, uint64_t idx, uint32_t thr, float ik, float (&m)[4]) {
+    dropout4(seed, site, idx, thr, ik, m);
+  }
+};
+template <> struct VecIO<8> {
+  static __device__ __forceinline__ void ld(const bf16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __bfloat1622float2(h[k]);
+      v[2 * k] = f.x;
+      v[2 * k + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    float a[4], b[4];
+    load4(p, a); load4(p + 4, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = a[k]; v[4 + k] = b[k]; }
+  }
+  static __device__ __forceinline__ void st(bf16* p, const float (&v)[8]) {
+    uint4 t;
+    t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  // same element -> mask mapping as two consecutive 4-wide groups, so VEC does not change results
+  static __device__ __forceinline__ void drop(uint64_t seed, uint64_t site, uint64_t idx8, uint32_t thr, float ik, float (&m)[8]) {
+    float a[4], b[4];
+    dropout4(seed, site, 2 * idx8, thr, ik, a);
+    dropout4(seed, site, 2 * idx8 + 1, thr, ik, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = a[k]; m[4 + k] = b[k]; }
+  }
+};
+
+template <typename T, int ITERS, int VEC>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ z_out, T* __restrict__ y, float* __restrict__ mean,
@@ -18,37 +63,37 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
   int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  int d4 = d >> 2;
+  int d4 = d / VEC;
   for (long long row = warp; row < rows; row += nwarps) {
-    float v[ITERS][4];
+    float v[ITERS][VEC];
     float s = 0.f;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       int c4 = lane + it * 32;
       if (c4 < d4) {
-        long long off = row * d + c4 * 4;
-        load4(branch + off, v[it]);
+        long long off = row * d + c4 * VEC;
+        VecIO<VEC>::ld(branch + off, v[it]);
         if (thr) {
-          float m[4];
-          dropout4(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
+          float m[VEC];
+          VecIO<VEC>::drop(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[it][k] *= m[k];
+          for (int k = 0; k < VEC; ++k) v[it][k] *= m[k];
         }
         if (resid) {
-          float r[4];
-          load4(resid + off, r);
+          float r[VEC];
+          VecIO<VEC>::ld(resid + off, r);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[it][k] += r[k];
+          for (int k = 0; k < VEC; ++k) v[it][k] += r[k];
         }
         if (z_out) {
-          store4(z_out + off, v[it]);
+          VecIO<VEC>::st(z_out + off, v[it]);
           // statistics are taken on the values as stored so that backward (which re-reads z)
           // sees exactly the same normalisation input
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[it][k] = to_f32(from_f32<T>(v[it][k]));
+          for (int k = 0; k < VEC; ++k) v[it][k] = to_f32(from_f32<T>(v[it][k]));
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s += v[it][k];
+        for (int k = 0; k < VEC; ++k) s += v[it][k];
       }
     }
     float mu = warp_sum(s) / d;
@@ -58,7 +103,7 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
       int c4 = lane + it * 32;
       if (c4 < d4) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < VEC; ++k) {
           float t = v[it][k] - mu;
           q += t * t;
         }
@@ -73,12 +118,12 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
     for (int it = 0; it < ITERS; ++it) {
       int c4 = lane + it * 32;
       if (c4 < d4) {
-        float g[4], b[4], o[4];
-        load4(gamma + c4 * 4, g);
-        load4(beta + c4 * 4, b);
+        float g[VEC], b[VEC], o[VEC];
+        VecIO<VEC>::ld(gamma + c4 * VEC, g);
+        VecIO<VEC>::ld(beta + c4 * VEC, b);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = (v[it][k] - mu) * rs * g[k] + b[k];
-        store4(y + row * d + c4 * 4, o);
+        for (int k = 0; k < VEC; ++k) o[k] = (v[it][k] - mu) * rs * g[k] + b[k];
+        VecIO<VEC>::st(y + row * d + c4 * VEC, o);
       }
     }
   }
@@ -86,7 +131,7 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
 
 // dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy.
 // d_branch = dz * dropmask (written only when dropout is on; otherwise the caller aliases dz).
-template <typename T, int ITERS>
+template <typename T, int ITERS, int VEC>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz,
@@ -97,28 +142,28 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   long long warp = (long long)blockIdx.x * nw + wib;
   long long nwarps = (long long)gridDim.x * nw;
-  int d4 = d >> 2;
-  float ag[ITERS][4], ab[ITERS][4], g[ITERS][4];
+  int d4 = d / VEC;
+  float ag[ITERS][VEC], ab[ITERS][VEC], g[ITERS][VEC];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     int c4 = lane + it * 32;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ag[it][k] = ab[it][k] = 0.f;
-    if (c4 < d4) load4(gamma + c4 * 4, g[it]);
+    for (int k = 0; k < VEC; ++k) ag[it][k] = ab[it][k] = 0.f;
+    if (c4 < d4) VecIO<VEC>::ld(gamma + c4 * VEC, g[it]);
   }
   for (long long row = warp; row < rows; row += nwarps) {
     float mu = mean[row], rs = rstd[row];
-    float xh[ITERS][4], gy[ITERS][4];
+    float xh[ITERS][VEC], gy[ITERS][VEC];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       int c4 = lane + it * 32;
       if (c4 < d4) {
-        float a[4], zz[4];
-        load4(dy + row * d + c4 * 4, a);
-        load4(z + row * d + c4 * 4, zz);
+        float a[VEC], zz[VEC];
+        VecIO<VEC>::ld(dy + row * d + c4 * VEC, a);
+        VecIO<VEC>::ld(z + row * d + c4 * VEC, zz);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < VEC; ++k) {
           xh[it][k] = (zz[k] - mu) * rs;
           ab[it][k] += a[k];
           ag[it][k] += a[k] * xh[it][k];
@@ -134,18 +179,18 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __
     for (int it = 0; it < ITERS; ++it) {
       int c4 = lane + it * 32;
       if (c4 < d4) {
-        float o[4];
+        float o[VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = rs * (gy[it][k] - s1 - xh[it][k] * s2);
-        store4(dz + row * d + c4 * 4, o);
+        for (int k = 0; k < VEC; ++k) o[k] = rs * (gy[it][k] - s1 - xh[it][k] * s2);
+        VecIO<VEC>::st(dz + row * d + c4 * VEC, o);
         if (dbranch) {
           if (thr) {
-            float m[4];
-            dropout4(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
+            float m[VEC];
+            VecIO<VEC>::drop(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] *= m[k];
+            for (int k = 0; k < VEC; ++k) o[k] *= m[k];
           }
-          store4(dbranch + row * d + c4 * 4, o);
+          VecIO<VEC>::st(dbranch + row * d + c4 * VEC, o);
         }
       }
     }
@@ -158,9 +203,9 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __
     int c4 = lane + it * 32;
     if (c4 < d4) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        sg[wib * d + c4 * 4 + k] = ag[it][k];
-        sb[wib * d + c4 * 4 + k] = ab[it][k];
+      for (int k = 0; k < VEC; ++k) {
+        sg[wib * d + c4 * VEC + k] = ag[it][k];
+        sb[wib * d + c4 * VEC + k] = ab[it][k];
       }
     }
   }
@@ -180,14 +225,16 @@ template <typename T>
 static int ln_fwd_launch(const void* branch, const void* resid, const float* gamma, const float* beta, void* z,
                          void* y, float* mean, float* rstd, long long rows, int d, float eps, uint32_t thr,
                          float inv_keep, uint64_t seed, uint64_t site, cudaStream_t st) {
-  int iters = (d / 4 + 31) / 32;
+  constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
+  if (d % VEC) { smer_set_error("smer_layernorm_fwd: d=%d must be a multiple of %d for this dtype", d, VEC); return SMER_ERR_ARG; }
+  int iters = (d / VEC + 31) / 32;
   long long blocks = (rows + 7) / 8;
   long long cap = (long long)smer_num_sms() * 8;
   int grid = (int)(blocks < cap ? blocks : cap);
   if (grid < 1) grid = 1;
 #define LN_CASE(I)                                                                                          \
   case I:                                                                                                   \
-    ln_fwd_kernel<T, I><<<grid, 256, 0, st>>>((const T*)branch, (const T*)resid, gamma, beta, (T*)z, (T*)y, mean, \
+    ln_fwd_kernel<T, I, VEC><<<grid, 256, 0, st>>>((const T*)branch, (const T*)resid, gamma, beta, (T*)z, (T*)y, mean, \
                                               rstd, rows, d, eps, thr, inv_keep, seed, site, smer_seed_dev()); \
     break;
   switch (iters) {
@@ -220,17 +267,19 @@ template <typename T>
 static int ln_bwd_launch(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
                          void* dz, void* dbranch, float* dgamma, float* dbeta, long long rows, int d, uint32_t thr,
                          float inv_keep, uint64_t seed, uint64_t site, cudaStream_t st) {
-  int iters = (d / 4 + 31) / 32;
+  constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
+  if (d % VEC) { smer_set_error("smer_layernorm_bwd: d=%d must be a multiple of %d for this dtype", d, VEC); return SMER_ERR_ARG; }
+  int iters = (d / VEC + 31) / 32;
   long long blocks = (rows + 7) / 8;
-  long long cap = (long long)smer_num_sms() * 2;
+  long long cap = (long long)smer_num_sms() * 4;
   int grid = (int)(blocks < cap ? blocks : cap);
   if (grid < 1) grid = 1;
   size_t smem = 2 * 8 * (size_t)d * sizeof(float);
 #define LN_CASE(I)                                                                                              \
   case I:                                                                                                       \
     if (smem > 48 * 1024)                                                                                       \
-      cudaFuncSetAttribute(ln_bwd_kernel<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    ln_bwd_kernel<T, I><<<grid, 256, smem, st>>>((const T*)dy, (const T*)z, mean, rstd, gamma, (T*)dz, (T*)dbranch, \
+      cudaFuncSetAttribute(ln_bwd_kernel<T, I, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    ln_bwd_kernel<T, I, VEC><<<grid, 256, smem, st>>>((const T*)dy, (const T*)z, mean, rstd, gamma, (T*)dz, (T*)dbranch, \
                                                  dgamma, dbeta, rows, d, thr, inv_keep, seed, site, smer_seed_dev()); \
     break;
   switch (iters) {

@@ -43,7 +43,10 @@ def test_engine_step_matches_oracle_fp32(oracle):
     for n, g in ref_grads.items():
         p = sd2[n].clone()
         O.adam_step(p, g, torch.zeros_like(p), torch.zeros_like(p), 1, lr=1e-3)
-        torch.testing.assert_close(dict(eng2_m.named_parameters())[n].detach().cpu(), p, rtol=2e-3, atol=1.5e-4)     # entries with |g| ~ eps move by O(lr)
+        mine = dict(eng2_m.named_parameters())[n].detach().cpu()
+        stable = g.abs() > 1e-5                 # where |g| ~ eps the Adam direction is ill-conditioned
+        torch.testing.assert_close(mine[stable], p[stable], rtol=2e-3, atol=5e-5)
+        assert (mine - sd2[n]).abs().max().item() <= 1.01e-3      # no entry moves by more than lr
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp32"])
