@@ -207,12 +207,22 @@ def run_train(args):
         dist.all_reduce(t)
         return float(t.item())
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     launches_per_step = None
     if use_graph:
         l0 = ops.LAUNCHES
-        eng.capture(B, S, T)                              # warm-up step + capture (two passes of launches)
-        launches_per_step = (ops.LAUNCHES - l0) // 2 + 3  # + arena memset, loss-sum memset, counter bump
+        try:
+            eng.capture(B, S, T)                          # warm-up step + capture (two passes of launches)
+            launches_per_step = (ops.LAUNCHES - l0) // 2 + 3  # + arena memset, loss-sum memset, counter bump
+        except Exception as e:                            # e.g. a collective that refuses capture: run eagerly
+            if rank == 0:
+                print(f"[bench] graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
+            use_graph = False
+    if world > 1:
+        flag = torch.tensor([1 if use_graph else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        use_graph = bool(flag.item())
+    if use_graph:
         step = lambda b: eng.step_graph(*b)
     else:
         step = lambda b: eng.step(*b)

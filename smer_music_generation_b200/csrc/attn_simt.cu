@@ -50,11 +50,11 @@ __device__ __forceinline__ float row_dot(const float (&a)[DPT], const float* __r
 }
 
 __device__ __forceinline__ void drop_lanes(const AttnParams& p, uint32_t rowkey, int j4, float (&m)[4]) {
-  uint32_t b0 = attn_pair_bits(rowkey, j4 * 4), b1 = attn_pair_bits(rowkey, j4 * 4 + 2);
-  m[0] = (b0 & 0xFFFFu) >= p.thr ? p.inv_keep : 0.f;
-  m[1] = (b0 >> 16) >= p.thr ? p.inv_keep : 0.f;
-  m[2] = (b1 & 0xFFFFu) >= p.thr ? p.inv_keep : 0.f;
-  m[3] = (b1 >> 16) >= p.thr ? p.inv_keep : 0.f;
+  uint32_t b0 = attn_pair_x(rowkey, j4 * 4), b1 = attn_pair_x(rowkey, j4 * 4 + 2);
+  m[0] = b0 >= p.thr ? p.inv_keep : 0.f;
+  m[1] = attn_odd(b0) >= p.thr ? p.inv_keep : 0.f;
+  m[2] = b1 >= p.thr ? p.inv_keep : 0.f;
+  m[3] = attn_odd(b1) >= p.thr ? p.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -386,7 +386,7 @@ static int fill_params(AttnParams& p, const smer_attn_args* a, const char* who) 
   p.addmask = a->add_mask; p.ldmask = a->ld_mask;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale = a->scale; p.causal = a->causal; p.q_pos0 = a->q_pos0;
-  p.thr = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;      // 16-bit threshold
+  p.thr = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;       // p * 2^32
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   if (p.B <= 0 || p.H <= 0 || p.Lq <= 0 || p.Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }

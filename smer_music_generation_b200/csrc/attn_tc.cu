@@ -41,7 +41,7 @@ struct FwdParams {
   int B, H, Lq, Lk;
   float c_log2;            // scale * log2(e)
   int causal;
-  uint32_t thr16;
+  uint32_t thr16;          // dropout threshold p * 2^32 (0 = dropout off)
   float inv_keep;
   uint64_t seed, site;
   const unsigned long long* seed_dev;
@@ -227,9 +227,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (p.thr16) {
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2) {
-            const uint32_t bits = attn_pair_bits(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2);
-            pv[2 * k2] = (bits & 0xFFFFu) >= p.thr16 ? pv[2 * k2] * p.inv_keep : 0.f;
-            pv[2 * k2 + 1] = (bits >> 16) >= p.thr16 ? pv[2 * k2 + 1] * p.inv_keep : 0.f;
+            const uint32_t x = attn_pair_x(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2);
+            pv[2 * k2] = x >= p.thr16 ? pv[2 * k2] * p.inv_keep : 0.f;
+            pv[2 * k2 + 1] = attn_odd(x) >= p.thr16 ? pv[2 * k2 + 1] * p.inv_keep : 0.f;
           }
         }
 #pragma unroll
@@ -304,7 +304,7 @@ struct BwdParams {
   int B, H, Lq, Lk;
   float c_log2, scale;
   int causal;
-  uint32_t thr16;
+  uint32_t thr16;          // dropout threshold p * 2^32 (0 = dropout off)
   float inv_keep;
   uint64_t seed, site;
   const unsigned long long* seed_dev;
@@ -481,8 +481,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (w != 0u) pr = ((w >> (sc * 16 + k)) & 1u) ? 0.f : pr;
             float dp = __uint_as_float(dv[k]);
             if (p.thr16) {
-              const uint32_t bits = attn_pair_bits(rowkey, j0 + cb + k);
-              dp = ((bits >> ((k & 1) * 16)) & 0xFFFFu) >= p.thr16 ? dp * p.inv_keep : 0.f;
+              uint32_t x = attn_pair_x(rowkey, j0 + cb + k);       // shared by k and k^1 (CSE)
+              if (k & 1) x = attn_odd(x);
+              dp = x >= p.thr16 ? dp * p.inv_keep : 0.f;
             }
             ds[k] = pr * (dp - dsum);
           }
@@ -625,7 +626,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t pd_row = ptx::smem_u32(sPd) + r * 128;
     const uint32_t ds_row = ptx::smem_u32(sdS) + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
-    const uint32_t jsh = (uint32_t)((j & 1) * 16);
     const long long rowbase = ((long long)b * p.H + h) * p.Lq;
     const float c2 = p.c_log2;
     for (int n = 0; n < ntiles; ++n) {
@@ -673,7 +673,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lv[u]));
             if (key_masked || col < cm) pr = 0.f;
             float keep = 1.f;
-            if (p.thr16) keep = ((attn_pair_bits(kk[u], j) >> jsh) & 0xFFFFu) >= p.thr16 ? p.inv_keep : 0.f;
+            if (p.thr16) keep = attn_keep(kk[u], j, p.thr16) ? p.inv_keep : 0.f;
             pd[k] = pr * keep;
             ds[k] = pr * (__uint_as_float(dv[k]) * keep - dd[u]);
           }
@@ -753,7 +753,7 @@ extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.c_log2 = a->scale * 1.4426950408889634f;
   p.causal = a->causal;
-  p.thr16 = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;
+  p.thr16 = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;      // p * 2^32 (full-word compare)
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   static bool attr_set = false;
@@ -787,7 +787,7 @@ extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   p.lse = a->lse; p.dsum = a->dsum; p.kv_len = a->kv_len; p.pad = a->key_pad;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.c_log2 = a->scale * 1.4426950408889634f; p.scale = a->scale; p.causal = a->causal;
-  p.thr16 = a->dropout_p > 0.f ? attn_dropout_thr16(a->dropout_p) : 0u;
+  p.thr16 = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;      // p * 2^32 (full-word compare)
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   static bool attr_set = false;

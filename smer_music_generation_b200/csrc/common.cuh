@@ -154,7 +154,7 @@ __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t site, uint64_t 
 // the (B,H,Lq,Lk) keep-mask is instead a counter hash: a 32-bit key per (seed, site, b, h, i)
 // row, then one avalanche mix per PAIR of keys giving two 16-bit uniforms.  The SIMT and
 // tcgen05 kernels (forward, backward, attention-weights) all call these, so they agree bit
-// for bit.  keep(j) = u16 >= thr16, thr16 = round(p * 65536).
+// for bit.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
@@ -167,18 +167,20 @@ __device__ __forceinline__ uint32_t attn_row_key(uint64_t seed, uint64_t site, l
   a = lowbias32(a + (uint32_t)((unsigned long long)rowid >> 32) + 0x632BE5ABu);
   return a;
 }
-// 32 bits for keys (j & ~1, j | 1): low half for the even key, high half for the odd one
-__device__ __forceinline__ uint32_t attn_pair_bits(uint32_t rowkey, int j) {
-  return lowbias32(rowkey + (uint32_t)(j >> 1) * 0x9E3779B9u);
+// One 32-bit word per PAIR of keys: two xorshift-multiply rounds of (rowkey + pair * golden
+// ratio) give the even key's uniform; the odd key's is one more multiply-add of it.  The keep test
+// compares the full 32-bit word with thr32 = p * 2^32 (no field extraction).  ALU-pipe cost is
+// what bounds the tcgen05 attention kernels (ncu: ALU 62 %), hence the frugality.
+__device__ __forceinline__ uint32_t attn_pair_x(uint32_t rowkey, int j) {
+  uint32_t x = rowkey + (uint32_t)(j >> 1) * 0x9E3779B9u;
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u;
+  return x;
 }
-__device__ __forceinline__ bool attn_keep(uint32_t rowkey, int j, uint32_t thr16) {
-  return ((attn_pair_bits(rowkey, j) >> ((j & 1) * 16)) & 0xFFFFu) >= thr16;
-}
-static inline uint32_t attn_dropout_thr16(float p) {
-  double t = (double)p * 65536.0 + 0.5;
-  if (t < 0) t = 0;
-  if (t > 65535.0) t = 65535.0;
-  return (uint32_t)t;
+__device__ __forceinline__ uint32_t attn_odd(uint32_t x) { return x * 0x297A2D39u + 0x7F4A7C15u; }
+__device__ __forceinline__ bool attn_keep(uint32_t rowkey, int j, uint32_t thr32) {
+  uint32_t x = attn_pair_x(rowkey, j);
+  if (j & 1) x = attn_odd(x);
+  return x >= thr32;
 }
 
 static inline uint32_t dropout_threshold(float p) {

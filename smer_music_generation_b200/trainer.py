@@ -186,9 +186,8 @@ class TrainEngine:
     def capture(self, B: int, S: int, T: int):
         """Captures one full step (forward, loss, backward, Adam) for fixed shapes.  The dropout
         seed and Adam's step number come from a device counter that the graph itself increments,
-        so every replay is a new training step.  Single-GPU only (collectives stay eager)."""
-        if self.world > 1:
-            raise RuntimeError("TrainEngine.capture: graph capture is single-GPU; use step() under DP")
+        so every replay is a new training step.  Under data parallelism the NCCL all-reduces (loss
+        sums, gradient buckets on the side stream) are captured into the same graph."""
         dev = self.dev
         self._g_in = dict(src=torch.zeros(B, S, dtype=torch.int64, device=dev),
                           tgt_in=torch.zeros(B, T, dtype=torch.int64, device=dev),
@@ -199,7 +198,8 @@ class TrainEngine:
         gi["src"].fill_(3); gi["tgt_in"].fill_(3); gi["tgt_out"].fill_(3)
         self._ctr = torch.full((1,), self.step_count, dtype=torch.int64, device=dev)
         K.check(K.lib().smer_set_seed_device_ptr(self._ctr.data_ptr()), "set_seed_device_ptr")
-        self._seed_base = (torch.initial_seed() * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        self._seed_base = (torch.initial_seed() * 0x9E3779B97F4A7C15
+                           + (0 if self.pg is None else 7919 * torch.distributed.get_rank(self.pg))) & 0xFFFFFFFFFFFFFFFF
         # warm-up outside capture (lazy kernel loads, cudaFuncSetAttribute), on a side stream
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

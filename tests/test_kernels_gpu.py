@@ -345,6 +345,44 @@ def test_attention_tc_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
         assert rel(grads["tc"][2].view(B, Lk, d), vr.grad) < 3e-2
 
 
+def test_attention_dropout_mask_statistics(dev):
+    """Keep-mask of the attention-probability dropout (counter hash in common.cuh): keep rate p,
+    no correlation between the two keys of a pair, neighbouring pairs, neighbouring rows, or sites."""
+    ops, K = _ops()
+    B, H, dh, L, p = 2, 1, 64, 512, 0.1
+    q = torch.zeros(B * L, dh, device=dev)                      # uniform attention: P = 1/L everywhere
+    k = torch.zeros(B * L, dh, device=dev)
+    v = torch.zeros(B * L, dh, device=dev)
+    o = torch.empty_like(q)
+    masks = []
+    for site in (1, 2):
+        lse = torch.empty(B, H, L, device=dev)
+        a = ops.attn_args(q, k, v, o, B, H, L, L, dh, lse=lse, dropout_p=p, seed=2024, site=site)
+        ops.attn_fwd(a)
+        w = torch.empty(B, L, L, device=dev)
+        ops.attn_weights(a, w)
+        masks.append((w > 0).float())
+    m = masks[0]
+    n = m.numel()
+    assert abs(m.mean().item() - (1 - p)) < 3e-3
+    assert abs(m[:, :, 0::2].mean().item() - (1 - p)) < 4e-3 and abs(m[:, :, 1::2].mean().item() - (1 - p)) < 4e-3
+
+    def corr(x, y):
+        x = x - x.mean()
+        y = y - y.mean()
+        return (x * y).mean().item() / (x.std().item() * y.std().item() + 1e-12)
+
+    tol = 5.0 / (n / 2) ** 0.5                                  # ~5 sigma for independent bits
+    assert abs(corr(m[:, :, 0::2], m[:, :, 1::2])) < tol        # even vs odd key of a pair
+    assert abs(corr(m[:, :, :-2], m[:, :, 2:])) < tol           # neighbouring pairs
+    assert abs(corr(m[:, :-1, :], m[:, 1:, :])) < tol           # neighbouring rows
+    assert abs(corr(m[0], m[1])) < tol                          # batches
+    assert abs(corr(masks[0], masks[1])) < tol                  # dropout sites
+    # row keep counts follow Binomial(L, 1-p): variance check
+    rows = m.sum(-1).flatten()
+    assert abs(rows.var().item() / (L * p * (1 - p)) - 1) < 0.25
+
+
 def test_attention_qpos_and_addmask(dev):
     ops, K = _ops()
     g = torch.Generator().manual_seed(9)
