@@ -371,6 +371,7 @@ def run_decode(args):
             gens.append(sum(res["generated"]))
     ms = sum(times)
     toks = float(sum(gens))
+    kl = dec.kernel_launches
     if world > 1:
         t = torch.tensor([ms, toks], dtype=torch.float64, device=dev)
         tm = t[:1].clone()
@@ -378,6 +379,17 @@ def run_decode(args):
         ts = t[1:].clone()
         dist.all_reduce(ts)
         ms, toks = float(tm.item()), float(ts.item())
+    # roofline of the dominant kernel (attention over the cross-attention K/V): one extra eager step
+    dec.use_graph = False
+    dec.generate(pieces, targets, seq_base=rank * per, max_steps=64, check_every=64)
+    pr = dec.profile_step()
+    pk = peaks()
+    ach = pr["cross"]["bytes"] / (pr["cross"]["ms"] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "decode_attn (cross-attention K/V)", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+            "avg_launch_ms": pr["cross"]["ms"] / max(1, pr["cross"]["launches"]),
+            "share_of_step": pr["cross"]["ms"] / pr["step_ms"], "eager_step_ms": pr["step_ms"],
+            "self_attn_gbs": pr["self"]["bytes"] / (pr["self"]["ms"] * 1e-3) / 1e9}
     if rank == 0:
         S = dec.S
         line = {"metric": METRIC_DECODE, "value": toks / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
@@ -388,7 +400,9 @@ def run_decode(args):
                            "timed": "whole generate(): H2D of pieces, encoder, cross-KV, decode loop, D2H of streams"},
                 "e2e": {"value": toks / (ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": dec.h2d_bytes,
                         "d2h_bytes_per_step": dec.d2h_bytes},
-                "gpu_launches": dec.kernel_launches, "decode_steps": res["steps"]}
+                "gpu_launches": kl, "decode_steps": res["steps"], "roofline": roof,
+                "step_ms_graph": ms / args.steps / max(1, res["steps"]),
+                "hbm_bytes_per_step_algorithmic": pr["cross"]["bytes"] + pr["self"]["bytes"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -208,6 +208,7 @@ class InfillDecoder:
         self.control_bitmap_host = bm
         self.steps_run = 0
         self.kernel_launches = 0
+        self.profile = None                 # list of (kind, start, end) CUDA events when profiling one eager step
 
     # -- state ------------------------------------------------------------------------
     def _setup(self, pieces, targets, nwd, seq_base):
@@ -269,6 +270,10 @@ class InfillDecoder:
 
     def _decode_attn(self, q, new_k, new_v, kc, vc, out, kv_len, key_pad, ld_cache, cache_stride, cache_len, ld_pad):
         m = self.m
+        prof = self.profile
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream())
         a = K.DecodeAttnArgs()
         a.q, a.new_k, a.new_v = q.data_ptr(), ops._p(new_k), ops._p(new_v)
         a.k_cache, a.v_cache, a.out = kc.data_ptr(), vc.data_ptr(), out.data_ptr()
@@ -279,6 +284,10 @@ class InfillDecoder:
         a.dtype = K.dt(q)
         a.scale = 1.0 / math.sqrt(m.d_model // m.nhead)
         K.check(K.lib().smer_decode_attn(C.byref(a), K.stream()), "decode_attn")
+        if prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream())
+            prof.append(("cross" if new_k is None else "self", e0, e1))
 
     def _step(self, step_idx_base: int):
         """One token for every unfinished piece.  All launches on the current stream; no sync."""
@@ -329,6 +338,27 @@ class InfillDecoder:
         a.out_token = a.out_probs = None
         K.check(lib.smer_sample_masked(C.byref(a), K.stream()), "sample_masked")
         self.launches_per_step = launches + 3
+
+    def profile_step(self):
+        """Runs ONE extra eager decode step (state is advanced by it) with CUDA events around the
+        attention launches; returns algorithmic HBM bytes and milliseconds per kind."""
+        self.profile = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pos = self.fed_len.clone()
+        e0.record()
+        self._step(0)
+        e1.record()
+        torch.cuda.synchronize()
+        d, esz = self.m.d_model, (2 if self.m.compute_dtype == torch.bfloat16 else 4)
+        nl = len(self.layer_p)
+        cross_bytes = float(self.src_len.sum().item()) * 2 * d * esz          # per layer: K and V rows of every piece
+        self_bytes = float((pos + 1).clamp(max=self.max_len).sum().item()) * 2 * d * esz
+        out = {"step_ms": e0.elapsed_time(e1)}
+        for kind, nbytes in (("cross", cross_bytes), ("self", self_bytes)):
+            ms = sum(a.elapsed_time(b) for k, a, b in self.profile if k == kind)
+            out[kind] = {"ms": ms, "bytes": nbytes * nl, "launches": sum(1 for k, _, _ in self.profile if k == kind)}
+        self.profile = None
+        return out
 
     # -- public -----------------------------------------------------------------------
     @torch.no_grad()
