@@ -291,7 +291,7 @@ def run_train(args):
     roof.update({"kernel": dom, "traffic": None, "peak_source": pk["src"] + " (sustained)",
                  "share_of_step": d["ms"] / tot_ms, "launches_per_step": d["launch_groups"],
                  "avg_launch_ms": d["ms"] / d["launch_groups"]})
-    step_flops = 3.0 * train_flops(B, S, T)
+    step_flops = 3.0 * train_flops(B, S, T, CFG['d'], CFG['ff'], CFG['le'], CFG['ld'])
     fam = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot_ms, 4),
                **({"tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} if k in tensor_fams else
                   {"gbs": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1)} if v["work"] else {})}
@@ -307,7 +307,7 @@ def run_train(args):
         line = {"metric": METRIC_TRAIN, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": f"configs[1]: default SMER transformer (d512 h8 4+4 layers ff2048 V309), teacher-forced "
+                "config": {"workload": f"{'configs[1]: default' if (CFG['d'], CFG['le'], B, S, T) == (512, 4, 32, 1024, 1024) else 'variant of configs[1]:'} SMER transformer (d{CFG['d']} h{CFG['nhead']} {CFG['le']}+{CFG['ld']} layers ff{CFG['ff']} V309), teacher-forced "
                                        f"train step fwd+loss+bwd+Adam, dropout 0.1, B{B}/GPU x S{S} (+T{T}), suffix padding "
                                        f"U[0.75L,L], tokens counted = non-pad src+tgt",
                            "l2": "working set per step (~3.5 GB activations) >> 126 MB L2; 4 rotating input batches",
@@ -424,7 +424,13 @@ def main():
     ap.add_argument("--splits", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--d-model", type=int, default=512)
+    ap.add_argument("--nhead", type=int, default=8)
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--ff", type=int, default=2048)
     args = ap.parse_args()
+    CFG.update(d=args.d_model, nhead=args.nhead, le=args.layers, ld=args.layers, ff=args.ff,
+               max_len=max(2400, args.seq, args.tgt))
     if args.warmup < 3 and args.impl == "ours" and args.workload == "train":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":

@@ -217,7 +217,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int u = 0; u < 8; ++u) bias8[u] = 0.f;
         if (p.bias && (!(p.flags & SMER_EPI_ATOMIC) || sp == 0)) load8(p.bias + col, bias8);
-#pragma unroll 2
+        // residual / gate operands of the round's 4 row-iterations: issue all loads up front, otherwise
+        // their latency serialises the epilogue past the MMA time of a K=512 tile
+        float rsv[4][8];
+        const bool has_r = p.resid != nullptr && !(p.flags & SMER_EPI_ATOMIC);
+        if (has_r) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = m0 + quarter * 32 + it * 8 + (lane >> 2);
+            if (row < p.M) load8(reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr + col, rsv[it]);
+          }
+        }
+#pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 8 + (lane >> 2);
           const int row = m0 + quarter * 32 + rl;
@@ -242,16 +253,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                          : "memory");
             continue;
           }
-          const TC* rrow = p.resid ? reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr : nullptr;
           if (p.flags & SMER_EPI_RELU) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
           }
           if (p.flags & SMER_EPI_GATE) {
-            float gte[8];
-            load8(rrow + col, gte);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = gte[u] > 0.f ? v[u] * p.inv_keep : 0.f;
+            for (int u = 0; u < 8; ++u) v[u] = rsv[it][u] > 0.f ? v[u] * p.inv_keep : 0.f;
           } else {
             if (p.thr) {
               float m0_[4], m1_[4];
@@ -261,11 +269,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
             }
-            if (rrow) {
-              float rs[8];
-              load8(rrow + col, rs);
+            if (has_r) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] += rs[u];
+              for (int u = 0; u < 8; ++u) v[u] += rsv[it][u];
             }
             if (p.flags & SMER_EPI_ACCUM) {
               float old[8];
