@@ -23,12 +23,21 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
-constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB per operand per stage
+constexpr int BM = 128, BK = 64;
+constexpr int TILE_BYTES = BM * BK * 2;                      // 16 KB: the A tile of a stage (and 128 rows of B)
 constexpr int GEMM_THREADS = 320;
 constexpr int EPI_WARPS = 8;
-constexpr int STAGE_EPI = 32 * 32 * 4;                        // per epilogue warp: 32 rows x 32 fp32 columns (two rounds per item)
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + EPI_WARPS * STAGE_EPI + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STAGE_EPI = 32 * 32 * 4;                        // per epilogue warp: 32 rows x 32 fp32 columns per round
+// Tile width BN is 256 when the problem has enough 128x256 tiles to fill the GPU (each A byte
+// fetched from L2 then feeds twice the MACs -- 128x128 tiles are L2-bandwidth-bound at ~1/3 of the
+// tensor peak), else 128.  Same smem budget either way: 6 x 32 KB or 4 x 48 KB stages.
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = TILE_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGE_EPI + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
 
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -77,14 +86,16 @@ struct EpiParams {
   int tiles_m, tiles_n, splits;          // work item w -> (split, m tile, n tile), n fastest
 };
 
-template <bool A_MN, bool B_MN, typename TC>
+template <bool A_MN, bool B_MN, typename TC, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int STAGES = Cfg<BN>::STAGES;
+  constexpr int B_BYTES = Cfg<BN>::B_BYTES;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TILE_BYTES;
-  uint8_t* sEpi = smem + 2 * STAGES * TILE_BYTES;
+  uint8_t* sEpi = smem + STAGES * Cfg<BN>::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + EPI_WARPS * STAGE_EPI);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
@@ -108,7 +119,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<256>(tmem_ptr);
+  if (warp == 1) ptx::tmem_alloc<Cfg<BN>::TMEM_COLS>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -124,10 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);
-          ptx::mbar_expect_tx(full_bar + s, 2 * TILE_BYTES);
+          ptx::mbar_expect_tx(full_bar + s, Cfg<BN>::STAGE_BYTES);
           const int k = kb * BK;
           uint8_t* a = sA + s * TILE_BYTES;
-          uint8_t* b = sB + s * TILE_BYTES;
+          uint8_t* b = sB + s * B_BYTES;
           if (!A_MN) {
             ptx::tma_load_2d(a, &tmap_a, full_bar + s, k, m0);
           } else {
@@ -135,10 +146,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::tma_load_2d(a + TILE_BYTES / 2, &tmap_a, full_bar + s, m0 + 64, k);
           }
           if (!B_MN) {
-            ptx::tma_load_2d(b, &tmap_b, full_bar + s, k, n0);
+            ptx::tma_load_2d(b, &tmap_b, full_bar + s, k, n0);                 // one box: BN rows x 64 k
           } else {
-            ptx::tma_load_2d(b, &tmap_b, full_bar + s, n0, k);
-            ptx::tma_load_2d(b + TILE_BYTES / 2, &tmap_b, full_bar + s, n0 + 64, k);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)                                   // 64-column chunks, 8 KB apart
+              ptx::tma_load_2d(b + c * (TILE_BYTES / 2), &tmap_b, full_bar + s, n0 + c * 64, k);
           }
         }
       }
@@ -160,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::mbar_wait(full_bar + s, (it / STAGES) & 1);
           ptx::tc_fence_after();
           const uint32_t a = ptx::smem_u32(sA + s * TILE_BYTES);
-          const uint32_t b = ptx::smem_u32(sB + s * TILE_BYTES);
+          const uint32_t b = ptx::smem_u32(sB + s * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: 16 elements = 32 B inside the 128 B swizzle row; rows 8 apart are 1024 B apart.
@@ -188,21 +200,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int acc = item & 1;
       ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * 64;
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32(t_addr, r0);
-      ptx::tmem_ld_32x32(t_addr + 32, r1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);   // accumulator is in registers: MMA may reuse it
-      // Two rounds of 32 columns: stage (lane == tile row; 16-byte chunk c of the 128-byte row goes to
-      // chunk c ^ (row & 7)), then drain with lane -> (row = it*8 + lane/4, 8 columns at (lane%4)*8):
-      // every store instruction covers 8 rows x 64 B (bf16) / 2 x 8 rows x 64 B (fp32).
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
+      // Rounds of 32 columns: TMEM -> registers, stage (lane == tile row; 16-byte chunk c of the
+      // 128-byte row goes to chunk c ^ (row & 7)), then drain with lane -> (row = it*8 + lane/4,
+      // 8 columns at (lane%4)*8): every store instruction covers 8 rows x 64 B (bf16).
       const int lc = (lane & 3) * 8;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const uint32_t* r = hh == 0 ? r0 : r1;
+#pragma unroll 1
+      for (int hh = 0; hh < BN / 64; ++hh) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + hh * 32, r);
+        ptx::tmem_ld_wait();
+        if (hh == BN / 64 - 1) {                               // whole accumulator part is in registers/smem
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);
+        }
         __syncwarp();                                          // previous round's staging reads are done
         {
           const uint32_t rowbase = stage_addr + lane * 128;
@@ -211,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             st_shared_v4(rowbase + (((uint32_t)c ^ (lane & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
         }
         __syncwarp();
-        const int col = n0 + chalf * 64 + hh * 32 + lc;
+        const int col = n0 + chalf * (BN / 2) + hh * 32 + lc;
         if (col >= p.N) continue;                              // N % 8 == 0
         float bias8[8];
 #pragma unroll
@@ -287,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<256>(tmem_base);
+  if (warp == 1) ptx::tmem_dealloc<Cfg<BN>::TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -367,14 +379,14 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
   return SMER_OK;
 }
 
-template <bool A_MN, bool B_MN, typename TC>
+template <bool A_MN, bool B_MN, typename TC, int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SMER_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SMER_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, TC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<A_MN, B_MN, TC><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tc_kernel<A_MN, B_MN, TC, BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
   return SMER_OK;
 }
 
@@ -392,10 +404,19 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   SMER_CHECK_ARG(!(flags & SMER_EPI_GATE) || resid, "smer_gemm_bf16_tc: gate epilogue needs the activation in `resid`");
   CUtensorMap ta, tb;
   int rc;
+  const int sms = smer_num_sms();
+  const int num_kb = (K + BK - 1) / BK;
+  if (split_k > num_kb) split_k = num_kb;
+  const int kb_per_split = (num_kb + split_k - 1) / split_k;
+  split_k = (num_kb + kb_per_split - 1) / kb_per_split;             // no empty splits
+  const int tiles_m = (M + BM - 1) / BM;
+  // 128x256 tiles when they still fill the GPU (and N is wide enough to use them)
+  const bool wide = N >= 256 && (long long)tiles_m * ((N + 255) / 256) * split_k >= sms;
+  const int bn = wide ? 256 : 128;
   if (a_kmajor) rc = smer_make_tmap_bf16(&ta, A, K, M, lda, BK, BM);
   else rc = smer_make_tmap_bf16(&ta, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (b_kmajor) rc = smer_make_tmap_bf16(&tb, B, K, N, ldb, BK, BN);
+  if (b_kmajor) rc = smer_make_tmap_bf16(&tb, B, K, N, ldb, BK, bn);
   else rc = smer_make_tmap_bf16(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   EpiParams p;
@@ -403,24 +424,23 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   p.thr = (dropout_p > 0.f && !(flags & SMER_EPI_GATE)) ? dropout_threshold(dropout_p) : 0u;
   p.inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   p.seed = seed; p.site = site; p.seed_dev = smer_seed_dev();
-  p.num_kb = (K + BK - 1) / BK;
-  if (split_k > p.num_kb) split_k = p.num_kb;
-  p.kb_per_split = (p.num_kb + split_k - 1) / split_k;
-  split_k = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;       // no empty splits
-  p.tiles_n = (N + BN - 1) / BN;
-  p.tiles_m = (M + BM - 1) / BM;
+  p.num_kb = num_kb;
+  p.kb_per_split = kb_per_split;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.tiles_m = tiles_m;
   p.splits = split_k;
   const long long total = (long long)p.tiles_n * p.tiles_m * split_k;
-  const int sms = smer_num_sms();
   dim3 grid((unsigned)(total < sms ? total : sms));
   cudaStream_t st = (cudaStream_t)stream;
   const bool amn = !a_kmajor, bmn = !b_kmajor, f32 = out_dtype == SMER_DT_F32;
-#define GO(AM, BMN, T) rc = launch_gemm<AM, BMN, T>(ta, tb, p, grid, st)
-  if (!amn && !bmn) { if (f32) GO(false, false, float); else GO(false, false, bf16); }
-  else if (!amn && bmn) { if (f32) GO(false, true, float); else GO(false, true, bf16); }
-  else if (amn && !bmn) { if (f32) GO(true, false, float); else GO(true, false, bf16); }
-  else { if (f32) GO(true, true, float); else GO(true, true, bf16); }
+#define GO2(AM, BMN, T) rc = wide ? launch_gemm<AM, BMN, T, 256>(ta, tb, p, grid, st) : launch_gemm<AM, BMN, T, 128>(ta, tb, p, grid, st)
+#define GO(AM, BMN) do { if (f32) GO2(AM, BMN, float); else GO2(AM, BMN, bf16); } while (0)
+  if (!amn && !bmn) GO(false, false);
+  else if (!amn && bmn) GO(false, true);
+  else if (amn && !bmn) GO(true, false);
+  else GO(true, true);
 #undef GO
+#undef GO2
   if (rc) return rc;
   SMER_CHECK_LAUNCH("smer_gemm_bf16_tc");
   return SMER_OK;
