@@ -129,23 +129,30 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr_lo, uint
 
 // keep-mask for 4 consecutive elements starting at element index `idx4*4` of dropout site
 // `site`: per-element multiplier (0 or 1/(1-p)).  Counter hash, not Philox: Philox4x32-10 is
-// ~100 instructions per 4 elements, which made the GEMM/LayerNorm epilogues ALU-bound; two
-// avalanche mixes of (seed, site, index) give four 16-bit uniforms for ~16 instructions.
-// `thr` = p * 2^32 (dropout_threshold); the compare uses its top 16 bits.
+// ~100 instructions per 4 elements, which made the GEMM/LayerNorm epilogues issue-bound.  One
+// two-round xorshift-multiply mix of (key + index) gives the first element's 32-bit uniform, the
+// other three are multiply-add steps of it; keep iff word >= thr, thr = p * 2^32.
 __device__ __forceinline__ uint32_t lowbias32_(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
   return x;
 }
+__device__ __forceinline__ uint32_t dropout_key(uint64_t seed, uint64_t site) {
+  return lowbias32_((uint32_t)seed ^ ((uint32_t)site * 0x9E3779B9u)) + (uint32_t)(seed >> 32);
+}
+__device__ __forceinline__ void dropout4k(uint32_t key, uint64_t idx4, uint32_t thr, float inv_keep, float (&m)[4]) {
+  uint32_t x = key + (uint32_t)idx4 * 0x9E3779B9u + (uint32_t)(idx4 >> 32) * 0x85EBCA6Bu;
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u;
+  m[0] = x >= thr ? inv_keep : 0.f;
+  x = x * 0x297A2D39u + 0x7F4A7C15u;
+  m[1] = x >= thr ? inv_keep : 0.f;
+  x = x * 0x297A2D39u + 0x7F4A7C15u;
+  m[2] = x >= thr ? inv_keep : 0.f;
+  x = x * 0x297A2D39u + 0x7F4A7C15u;
+  m[3] = x >= thr ? inv_keep : 0.f;
+}
 __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t site, uint64_t idx4, uint32_t thr,
                                          float inv_keep, float (&m)[4]) {
-  const uint32_t key = lowbias32_((uint32_t)seed ^ ((uint32_t)site * 0x9E3779B9u)) + (uint32_t)(seed >> 32);
-  const uint32_t a = lowbias32_(key ^ (uint32_t)idx4) + (uint32_t)(idx4 >> 32) * 0x85EBCA6Bu;
-  const uint32_t b0 = lowbias32_(a), b1 = lowbias32_(a ^ 0x68E31DA4u);
-  const uint32_t t16 = thr >> 16;
-  m[0] = (b0 & 0xFFFFu) >= t16 ? inv_keep : 0.f;
-  m[1] = (b0 >> 16) >= t16 ? inv_keep : 0.f;
-  m[2] = (b1 & 0xFFFFu) >= t16 ? inv_keep : 0.f;
-  m[3] = (b1 >> 16) >= t16 ? inv_keep : 0.f;
+  dropout4k(dropout_key(seed, site), idx4, thr, inv_keep, m);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -11,7 +11,8 @@
 #include "common.cuh"
 #include "../../include/smer_b200.h"
 
-constexpr int DEC_THREADS = 128;
+constexpr int DEC_THREADS = 128;          // long key ranges (cross-attention K/V): 16 key rows per CTA iteration
+constexpr int DEC_THREADS_SHORT = 32;     // short ranges (the growing self-attention cache): one warp per (piece, head)
 
 template <typename T, int EPL>
 __device__ __forceinline__ void load_row(const T* p, float (&v)[EPL]) {
@@ -36,11 +37,11 @@ __device__ __forceinline__ void load_row<bf16, 8>(const bf16* p, float (&v)[8]) 
     v[2 * k + 1] = f.y;
   }
 }
-template <typename T, int DH>
-__global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(smer_decode_attn_args a) {
+template <typename T, int DH, int THREADS>
+__global__ void __launch_bounds__(THREADS) decode_attn_kernel(smer_decode_attn_args a) {
   constexpr int EPL = DH >= 64 ? 8 : 4;          // elements per lane
   constexpr int LPK = DH / EPL;                  // lanes per key row (8, or 4 for dh=16)
-  constexpr int DEC_GROUPS = DEC_THREADS / LPK;  // key rows in flight per CTA iteration
+  constexpr int DEC_GROUPS = THREADS / LPK;      // key rows in flight per CTA iteration
   __shared__ float sm_m[DEC_GROUPS], sm_l[DEC_GROUPS];
   __shared__ float sm_acc[DEC_GROUPS][DH];
   int h = blockIdx.x, s = blockIdx.y, sp = blockIdx.z;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(smer_decode_at
 #pragma unroll
   for (int c = 0; c < EPL; ++c) sm_acc[grp][lig * EPL + c] = acc[c];
   __syncthreads();
-  if (tid < DH) {
+  for (int c = tid; c < DH; c += THREADS) {
     float M = -INFINITY;
 #pragma unroll
     for (int g = 0; g < DEC_GROUPS; ++g) M = fmaxf(M, sm_m[g]);
@@ -127,16 +128,16 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_attn_kernel(smer_decode_at
       for (int g = 0; g < DEC_GROUPS; ++g) {
         float w = expf(sm_m[g] - M);
         L += w * sm_l[g];
-        o += w * sm_acc[g][tid];
+        o += w * sm_acc[g][c];
       }
     }
     if (a.splits == 1) {
       T* out = (T*)a.out + (long long)s * a.ldo + h * DH;
-      out[tid] = from_f32<T>(L > 0.f ? o / L : 0.f);
+      out[c] = from_f32<T>(L > 0.f ? o / L : 0.f);
     } else {
       float* w = a.workspace + (((long long)s * gridDim.x + h) * a.splits + sp) * (DH + 2);
-      w[2 + tid] = o;
-      if (tid == 0) { w[0] = M; w[1] = L; }
+      w[2 + c] = o;
+      if (c == 0) { w[0] = M; w[1] = L; }
     }
   }
 }
@@ -166,9 +167,16 @@ template <typename T>
 static int decode_launch(const smer_decode_attn_args& a, cudaStream_t st) {
   dim3 grid(a.H, a.n_seq, a.splits);
   switch (a.dh) {
-    case 16: decode_attn_kernel<T, 16><<<grid, DEC_THREADS, 0, st>>>(a); break;
-    case 32: decode_attn_kernel<T, 32><<<grid, DEC_THREADS, 0, st>>>(a); break;
-    case 64: decode_attn_kernel<T, 64><<<grid, DEC_THREADS, 0, st>>>(a); break;
+    case 16: decode_attn_kernel<T, 16, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a); break;
+    case 32: decode_attn_kernel<T, 32, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a); break;
+    case 64:
+      // the self-attention cache (new_k given) holds at most cache_len keys, usually a few hundred:
+      // one warp per (piece, head) avoids paying a 128-thread CTA's fixed costs for a handful of keys
+      if (a.new_k && a.cache_len <= 2048 && a.splits == 1)
+        decode_attn_kernel<T, 64, DEC_THREADS_SHORT><<<grid, DEC_THREADS_SHORT, 0, st>>>(a);
+      else
+        decode_attn_kernel<T, 64, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a);
+      break;
     default: smer_set_error("smer_decode_attn: head dim %d unsupported (16/32/64)", a.dh); return SMER_ERR_UNSUPPORTED;
   }
   if (a.splits > 1) {

@@ -86,7 +86,11 @@ struct EpiParams {
   int tiles_m, tiles_n, splits;          // work item w -> (split, m tile, n tile), n fastest
 };
 
-template <bool A_MN, bool B_MN, typename TC, int BN>
+// Epilogue variants.  EPI_GENERIC reads the flags at run time; the others fix them at compile time
+// (the per-element flag branches and dead operand loads were ~1/3 of the epilogue's instructions).
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RELU_DROP = 3, EPI_RESID = 4, EPI_GATE = 5, EPI_ATOMIC = 6 };
+
+template <bool A_MN, bool B_MN, typename TC, int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -190,7 +194,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     const int quarter = warp & 3;
-    const uint64_t seed = (p.thr && !(p.flags & SMER_EPI_GATE)) ? eff_seed(p.seed, p.seed_dev) : 0ull;
+    const bool f_atomic = EPI == EPI_GENERIC ? (p.flags & SMER_EPI_ATOMIC) != 0 : EPI == EPI_ATOMIC;
+    const bool f_gate = EPI == EPI_GENERIC ? (p.flags & SMER_EPI_GATE) != 0 : EPI == EPI_GATE;
+    const bool f_relu = EPI == EPI_GENERIC ? (p.flags & SMER_EPI_RELU) != 0 : (EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RELU_DROP);
+    const bool f_drop = EPI == EPI_GENERIC ? (p.thr != 0u && !f_gate) : EPI == EPI_BIAS_RELU_DROP;
+    const bool f_bias = EPI == EPI_GENERIC ? p.bias != nullptr : (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RELU_DROP);
+    const bool f_accum = EPI == EPI_GENERIC ? (p.flags & SMER_EPI_ACCUM) != 0 : false;
+    const bool has_r = EPI == EPI_GENERIC ? (p.resid != nullptr && !f_atomic) : (EPI == EPI_RESID || EPI == EPI_GATE);
+    const uint32_t dkey = f_drop ? dropout_key(eff_seed(p.seed, p.seed_dev), p.site) : 0u;
     const int chalf = (warp - 2) >> 2;              // which 64 of the tile's 128 columns
     const uint32_t stage_addr = ptx::smem_u32(sEpi + (warp - 2) * STAGE_EPI);
     int item = 0;
@@ -198,14 +209,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
       const int m0 = (rem / p.tiles_n) * BM, n0 = (rem % p.tiles_n) * BN;
       const int acc = item & 1;
+      // bias of this warp's columns: issued before the accumulator wait so its latency is hidden
+      const int lc = (lane & 3) * 8;
+      float biasr[BN / 64][8];
+#pragma unroll
+      for (int hh = 0; hh < BN / 64; ++hh) {
+        const int colb = n0 + chalf * (BN / 2) + hh * 32 + lc;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) biasr[hh][u] = 0.f;
+        if (f_bias && (!f_atomic || sp == 0) && colb < p.N) load8(p.bias + colb, biasr[hh]);
+      }
       ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
       // Rounds of 32 columns: TMEM -> registers, stage (lane == tile row; 16-byte chunk c of the
       // 128-byte row goes to chunk c ^ (row & 7)), then drain with lane -> (row = it*8 + lane/4,
       // 8 columns at (lane%4)*8): every store instruction covers 8 rows x 64 B (bf16).
-      const int lc = (lane & 3) * 8;
-#pragma unroll 1
+#pragma unroll
       for (int hh = 0; hh < BN / 64; ++hh) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_addr + hh * 32, r);
@@ -225,14 +245,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         __syncwarp();
         const int col = n0 + chalf * (BN / 2) + hh * 32 + lc;
         if (col >= p.N) continue;                              // N % 8 == 0
-        float bias8[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) bias8[u] = 0.f;
-        if (p.bias && (!(p.flags & SMER_EPI_ATOMIC) || sp == 0)) load8(p.bias + col, bias8);
         // residual / gate operands of the round's 4 row-iterations: issue all loads up front, otherwise
         // their latency serialises the epilogue past the MMA time of a K=512 tile
         float rsv[4][8];
-        const bool has_r = p.resid != nullptr && !(p.flags & SMER_EPI_ATOMIC);
         if (has_r) {
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -252,10 +267,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ld_shared_v4(rowbase + ((c0 ^ (rl & 7)) << 4), v);
             ld_shared_v4(rowbase + (((c0 + 1) ^ (rl & 7)) << 4), v + 4);
           }
+          if (f_bias) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] += bias8[u];
+            for (int u = 0; u < 8; ++u) v[u] += biasr[hh][u];
+          }
           TC* crow = reinterpret_cast<TC*>(p.C) + (long long)row * p.ldc;
-          if (p.flags & SMER_EPI_ATOMIC) {
+          if (f_atomic) {
             float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                          "f"(v[3])
@@ -265,19 +282,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                          : "memory");
             continue;
           }
-          if (p.flags & SMER_EPI_RELU) {
+          if (f_relu) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
           }
-          if (p.flags & SMER_EPI_GATE) {
+          if (f_gate) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = rsv[it][u] > 0.f ? v[u] * p.inv_keep : 0.f;
           } else {
-            if (p.thr) {
+            if (f_drop) {
               float m0_[4], m1_[4];
               const uint64_t e4 = (uint64_t)(((long long)row * p.ldc + col) >> 2);
-              dropout4(seed, p.site, e4, p.thr, p.inv_keep, m0_);
-              dropout4(seed, p.site, e4 + 1, p.thr, p.inv_keep, m1_);
+              dropout4k(dkey, e4, p.thr, p.inv_keep, m0_);
+              dropout4k(dkey, e4 + 1, p.thr, p.inv_keep, m1_);
 #pragma unroll
               for (int u = 0; u < 4; ++u) { v[u] *= m0_[u]; v[4 + u] *= m1_[u]; }
             }
@@ -285,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] += rsv[it][u];
             }
-            if (p.flags & SMER_EPI_ACCUM) {
+            if (f_accum) {
               float old[8];
               load8(crow + col, old);
 #pragma unroll
@@ -379,14 +396,14 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
   return SMER_OK;
 }
 
-template <bool A_MN, bool B_MN, typename TC, int BN>
+template <bool A_MN, bool B_MN, typename TC, int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SMER_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, TC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    SMER_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, TC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<A_MN, B_MN, TC, BN><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tc_kernel<A_MN, B_MN, TC, BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
   return SMER_OK;
 }
 
@@ -433,14 +450,32 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   dim3 grid((unsigned)(total < sms ? total : sms));
   cudaStream_t st = (cudaStream_t)stream;
   const bool amn = !a_kmajor, bmn = !b_kmajor, f32 = out_dtype == SMER_DT_F32;
-#define GO2(AM, BMN, T) rc = wide ? launch_gemm<AM, BMN, T, 256>(ta, tb, p, grid, st) : launch_gemm<AM, BMN, T, 128>(ta, tb, p, grid, st)
-#define GO(AM, BMN) do { if (f32) GO2(AM, BMN, float); else GO2(AM, BMN, bf16); } while (0)
-  if (!amn && !bmn) GO(false, false);
-  else if (!amn && bmn) GO(false, true);
-  else if (amn && !bmn) GO(true, false);
-  else GO(true, true);
-#undef GO
-#undef GO2
+  // epilogue variant: the specialised ones cover the shapes the transformer stack launches
+  int epi = EPI_GENERIC;
+  if ((flags & SMER_EPI_ATOMIC) && !bias && flags == SMER_EPI_ATOMIC) epi = EPI_ATOMIC;
+  else if ((flags & SMER_EPI_GATE) && !bias && flags == SMER_EPI_GATE) epi = EPI_GATE;
+  else if (flags == 0 && resid && !bias && !p.thr) epi = EPI_RESID;
+  else if (flags == SMER_EPI_RELU && bias && !resid) epi = p.thr ? EPI_BIAS_RELU_DROP : EPI_BIAS_RELU;
+  else if (flags == 0 && bias && !resid && !p.thr) epi = EPI_BIAS;
+#define GO3(AM, BMN, T, E) (wide ? launch_gemm<AM, BMN, T, 256, E>(ta, tb, p, grid, st) : launch_gemm<AM, BMN, T, 128, E>(ta, tb, p, grid, st))
+  if (!amn && !bmn) {                       // nn.Linear forward
+    if (f32) rc = epi == EPI_BIAS ? GO3(false, false, float, EPI_BIAS) : GO3(false, false, float, EPI_GENERIC);
+    else if (epi == EPI_BIAS) rc = GO3(false, false, bf16, EPI_BIAS);
+    else if (epi == EPI_BIAS_RELU) rc = GO3(false, false, bf16, EPI_BIAS_RELU);
+    else if (epi == EPI_BIAS_RELU_DROP) rc = GO3(false, false, bf16, EPI_BIAS_RELU_DROP);
+    else rc = GO3(false, false, bf16, EPI_GENERIC);
+  } else if (!amn && bmn) {                 // input gradient
+    if (f32) rc = GO3(false, true, float, EPI_GENERIC);
+    else if (epi == EPI_RESID) rc = GO3(false, true, bf16, EPI_RESID);
+    else if (epi == EPI_GATE) rc = GO3(false, true, bf16, EPI_GATE);
+    else rc = GO3(false, true, bf16, EPI_GENERIC);
+  } else if (amn && bmn) {                  // weight gradient
+    if (f32) rc = epi == EPI_ATOMIC ? GO3(true, true, float, EPI_ATOMIC) : GO3(true, true, float, EPI_GENERIC);
+    else rc = GO3(true, true, bf16, EPI_GENERIC);
+  } else {
+    rc = f32 ? GO3(true, false, float, EPI_GENERIC) : GO3(true, false, bf16, EPI_GENERIC);
+  }
+#undef GO3
   if (rc) return rc;
   SMER_CHECK_LAUNCH("smer_gemm_bf16_tc");
   return SMER_OK;
