@@ -67,9 +67,10 @@ int smer_embed_bwd(const int64_t* ids, const void* dout, int dtype, float* demb,
 int smer_layernorm_fwd(const void* branch, const void* resid, const float* gamma, const float* beta,
                        void* z_out, void* y, float* mean, float* rstd, int dtype, long long rows, int d,
                        float eps, float dropout_p, uint64_t seed, uint64_t site, void* stream);
+/* dbias (nullable): += column sums of the branch gradient = bias gradient of the Linear feeding the branch */
 int smer_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
-                       void* dz, void* dbranch, float* dgamma, float* dbeta, int dtype, long long rows, int d,
-                       float dropout_p, uint64_t seed, uint64_t site, void* stream);
+                       void* dz, void* dbranch, float* dgamma, float* dbeta, float* dbias, int dtype, long long rows,
+                       int d, float dropout_p, uint64_t seed, uint64_t site, void* stream);
 
 /* ---- K2/K3/K6/K7/K9: nn.Linear products (transformer.py:362-364, model.py:82) --------------- */
 /* CUDA-core fp32-accumulate GEMM, arbitrary strides: C[m,n] = epi(sum_k A[m*sam+k*sak]*B[n*sbn+k*sbk]) */

@@ -56,7 +56,7 @@ _SIGS = {
     "smer_embed_pe_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _u64, _vp]),
     "smer_embed_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _f, _u64, _u64, _vp]),
     "smer_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _f, _u64, _u64, _vp]),
-    "smer_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _u64, _u64, _vp]),
+    "smer_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _u64, _u64, _vp]),
     "smer_gemm_simt": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _ll, _i, _f, _u64,
                             _u64, _i, _vp]),
     "smer_gemm_bf16_tc": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _f, _u64,

@@ -52,6 +52,16 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Blackwell packed fp32 math (FFMA2 / FADD2 / FMUL2) and 3-input max (FMNMX3): the softmax threads
+// are issue-bound (ncu: ~12 instructions per score element), so every halved instruction counts.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -195,7 +205,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t w = mw[c];
         if (w == 0u) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+          for (int k = 0; k < 32; k += 2) mx = max3(mx, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
         } else {
 #pragma unroll
           for (int k = 0; k < 32; ++k) mx = fmaxf(mx, ((w >> k) & 1u) ? -INFINITY : __uint_as_float(v[k]));
@@ -208,8 +218,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float m_new = fmaxf(m, mx * c2);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2(m - m_use);
-      float lsum = 0.f;
+      f32x2 lsum2 = pack2(0.f, 0.f);
+      const f32x2 c2p = pack2(c2, c2), nm2 = pack2(-m_use, -m_use);
       // ---- pass 2: P = exp2(S*c - m), row sum, dropout, bf16 pack into the swizzled A-operand tile
+      // (dropout keeps P unscaled here: the 1/(1-p) factor is folded into the final O normalisation)
 #pragma unroll
       for (int sc = 0; sc < 4; ++sc) {
         uint32_t v[16];
@@ -218,24 +230,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t w = mw[sc >> 1] >> ((sc & 1) * 16);
         float pv[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          float sval = __uint_as_float(v[k]);
-          if ((w & 0xFFFFu) != 0u) sval = ((w >> k) & 1u) ? -INFINITY : sval;
-          pv[k] = ex2(fmaf(sval, c2, -m_use));
-          lsum += pv[k];
+        for (int k = 0; k < 16; k += 2) {
+          float s0 = __uint_as_float(v[k]), s1 = __uint_as_float(v[k + 1]);
+          if ((w & 0xFFFFu) != 0u) {
+            s0 = ((w >> k) & 1u) ? -INFINITY : s0;
+            s1 = ((w >> (k + 1)) & 1u) ? -INFINITY : s1;
+          }
+          float e0, e1;
+          unpack2(fma2(pack2(s0, s1), c2p, nm2), e0, e1);
+          pv[k] = ex2(e0);
+          pv[k + 1] = ex2(e1);
+          lsum2 = add2(lsum2, pack2(pv[k], pv[k + 1]));
         }
         if (p.thr16) {
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2) {
             const uint32_t x = attn_pair_x(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2);
-            pv[2 * k2] = x >= p.thr16 ? pv[2 * k2] * p.inv_keep : 0.f;
-            pv[2 * k2 + 1] = attn_odd(x) >= p.thr16 ? pv[2 * k2 + 1] * p.inv_keep : 0.f;
+            pv[2 * k2] = x >= p.thr16 ? pv[2 * k2] : 0.f;
+            pv[2 * k2 + 1] = attn_odd(x) >= p.thr16 ? pv[2 * k2 + 1] : 0.f;
           }
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) st_row_chunk_fwd(sP_row, rx, (uint32_t)(sc * 2 + q), pv + 8 * q);
       }
-      l = l * alpha + lsum;
+      {
+        float ls0, ls1;
+        unpack2(lsum2, ls0, ls1);
+        l = l * alpha + (ls0 + ls1);
+      }
       m = m_new;
       ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core
       ptx::tc_fence_before();            // orders this thread's tcgen05.ld before the next MMAs
@@ -247,8 +269,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t v[32];
         ptx::tmem_ld_32x32(lane_addr + O_COL + hf * 32, v);
         ptx::tmem_ld_wait();
+        const f32x2 al2 = pack2(alpha, alpha);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc[k] = fmaf(acc[k], alpha, __uint_as_float(v[k]));
+        for (int k = 0; k < 32; k += 2)
+          unpack2(fma2(pack2(acc[k], acc[k + 1]), al2, pack2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]))), acc[k], acc[k + 1]);
       }
     }
     // row sum = both halves
@@ -257,7 +281,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bar_sync_bwd();
     l += xch[(hf ^ 1) * 128 + r];
     if (row_ok) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const float inv = l > 0.f ? p.inv_keep / l : 0.f;      // dropout's 1/(1-p) applied once per row
       bf16* orow = p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH + hf * 32;
 #pragma unroll
       for (int c = 0; c < 32; c += 8) {
@@ -467,6 +491,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::tc_fence_after();
       {
         const uint32_t w = mw[hf];
+        const f32x2 c2p = pack2(c2, c2), nl2 = pack2(-lse2, -lse2), ik2 = pack2(p.inv_keep, p.inv_keep), nd2 = pack2(-dsum, -dsum);
 #pragma unroll
         for (int sc = 0; sc < 2; ++sc) {               // two 16-column sub-chunks keep the register count low
           const int cb = hf * 32 + sc * 16;
@@ -476,16 +501,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ptx::tmem_ld_wait();
           float ds[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lse2));
-            if (w != 0u) pr = ((w >> (sc * 16 + k)) & 1u) ? 0.f : pr;
-            float dp = __uint_as_float(dv[k]);
-            if (p.thr16) {
-              uint32_t x = attn_pair_x(rowkey, j0 + cb + k);       // shared by k and k^1 (CSE)
-              if (k & 1) x = attn_odd(x);
-              dp = x >= p.thr16 ? dp * p.inv_keep : 0.f;
+          for (int k = 0; k < 16; k += 2) {
+            float e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, nl2), e0, e1);
+            float p0 = ex2(e0), p1 = ex2(e1);
+            if (w != 0u) {
+              p0 = ((w >> (sc * 16 + k)) & 1u) ? 0.f : p0;
+              p1 = ((w >> (sc * 16 + k + 1)) & 1u) ? 0.f : p1;
             }
-            ds[k] = pr * (dp - dsum);
+            float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
+            if (p.thr16) {
+              const uint32_t x = attn_pair_x(rowkey, j0 + cb + k);
+              d0 = x >= p.thr16 ? d0 : 0.f;
+              d1 = attn_odd(x) >= p.thr16 ? d1 : 0.f;
+            }
+            // dS = P * (dP * keep/(1-p) - D)
+            unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
           }
 #pragma unroll
           for (int q = 0; q < 2; ++q) st_row_chunk(row_addr, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
@@ -657,6 +688,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
         ptx::tmem_ld_wait();
         float pd[16], ds[16];
+        const f32x2 c2p = pack2(c2, c2), ik2 = pack2(p.inv_keep, p.inv_keep);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
           const int colb = cb + k4 * 4;
@@ -667,15 +699,25 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
           const uint32_t kk[4] = {key4.x, key4.y, key4.z, key4.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 4; u += 2) {
             const int k = k4 * 4 + u;
             const int col = colb + u;
-            float pr = ex2(fmaf(__uint_as_float(sv[k]), c2, -lv[u]));
-            if (key_masked || col < cm) pr = 0.f;
-            float keep = 1.f;
-            if (p.thr16) keep = attn_keep(kk[u], j, p.thr16) ? p.inv_keep : 0.f;
-            pd[k] = pr * keep;
-            ds[k] = pr * (__uint_as_float(dv[k]) * keep - dd[u]);
+            float e0, e1;
+            unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, pack2(-lv[u], -lv[u + 1])), e0, e1);
+            float p0 = ex2(e0), p1 = ex2(e1);
+            if (key_masked || col < cm) p0 = 0.f;
+            if (key_masked || col + 1 < cm) p1 = 0.f;
+            float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
+            float q0 = p0, q1 = p1;                       // P^T * keep (unscaled: 1/(1-p) folded into dV's final scale)
+            if (p.thr16) {
+              const bool k0 = attn_keep(kk[u], j, p.thr16), k1 = attn_keep(kk[u + 1], j, p.thr16);
+              q0 = k0 ? p0 : 0.f; q1 = k1 ? p1 : 0.f;
+              d0 = k0 ? d0 : 0.f; d1 = k1 ? d1 : 0.f;
+            }
+            pd[k] = q0;
+            pd[k + 1] = q1;
+            // dS^T = P * (dP * keep/(1-p) - D)
+            unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
           }
         }
 #pragma unroll
@@ -695,7 +737,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
     for (int part = 0; part < 2; ++part) {           // 0: dK (scaled), 1: dV; this thread's 32 columns
       bf16* drow = (part == 0 ? p.dk + ((long long)b * p.Lk + j) * p.lddk : p.dv + ((long long)b * p.Lk + j) * p.lddv) + h * DH + hf * 32;
-      const float sc = part == 0 ? p.scale : 1.f;
+      const float sc = part == 0 ? p.scale : p.inv_keep;      // dV: dropout's 1/(1-p) applied once here
       uint32_t v[32];
       if (ntiles > 0) {
         ptx::tmem_ld_32x32(lane_addr + 128 + part * 64 + hf * 32, v);

@@ -54,7 +54,7 @@ template <> struct VecIO<8> {
 };
 
 template <typename T, int ITERS, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ z_out, T* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, long long rows, int d, float eps, uint32_t thr, float inv_keep,
@@ -131,24 +131,27 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
 
 // dz = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += dy*xhat; dbeta += dy.
 // d_branch = dz * dropmask (written only when dropout is on; otherwise the caller aliases dz).
+// dbias (optional) += column sums of d_branch: the bias gradient of the nn.Linear that produced
+// the branch (out_proj / linear2), so no separate pass over d_branch is needed for it.
 template <typename T, int ITERS, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz,
-              T* __restrict__ dbranch, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int d,
+              T* __restrict__ dbranch, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dbias, long long rows, int d,
               uint32_t thr, float inv_keep, uint64_t seed, uint64_t site, const unsigned long long* seed_dev) {
   seed = eff_seed(seed, seed_dev);
-  extern __shared__ float sm[];   // [2][warps][d]
+  extern __shared__ float sm[];   // [3][warps][d]
   int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   long long warp = (long long)blockIdx.x * nw + wib;
   long long nwarps = (long long)gridDim.x * nw;
   int d4 = d / VEC;
-  float ag[ITERS][VEC], ab[ITERS][VEC], g[ITERS][VEC];
+  float ag[ITERS][VEC], ab[ITERS][VEC], ad[ITERS][VEC], g[ITERS][VEC];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     int c4 = lane + it * 32;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) ag[it][k] = ab[it][k] = 0.f;
+    for (int k = 0; k < VEC; ++k) ag[it][k] = ab[it][k] = ad[it][k] = 0.f;
     if (c4 < d4) VecIO<VEC>::ld(gamma + c4 * VEC, g[it]);
   }
   for (long long row = warp; row < rows; row += nwarps) {
@@ -192,12 +195,17 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __
           }
           VecIO<VEC>::st(dbranch + row * d + c4 * VEC, o);
         }
+        if (dbias) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) ad[it][k] += o[k];
+        }
       }
     }
   }
   // block reduction of the column sums, then one atomic per column per block
   float* sg = sm;
   float* sb = sm + nw * d;
+  float* sd = sm + 2 * nw * d;
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
     int c4 = lane + it * 32;
@@ -206,18 +214,21 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __
       for (int k = 0; k < VEC; ++k) {
         sg[wib * d + c4 * VEC + k] = ag[it][k];
         sb[wib * d + c4 * VEC + k] = ab[it][k];
+        if (dbias) sd[wib * d + c4 * VEC + k] = ad[it][k];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float tg = 0.f, tb = 0.f;
+    float tg = 0.f, tb = 0.f, td = 0.f;
     for (int w = 0; w < nw; ++w) {
       tg += sg[w * d + c];
       tb += sb[w * d + c];
+      if (dbias) td += sd[w * d + c];
     }
     atomicAdd(dgamma + c, tg);
     atomicAdd(dbeta + c, tb);
+    if (dbias) atomicAdd(dbias + c, td);
   }
 }
 
@@ -265,7 +276,7 @@ extern "C" int smer_layernorm_fwd(const void* branch, const void* resid, const f
 
 template <typename T>
 static int ln_bwd_launch(const void* dy, const void* z, const float* mean, const float* rstd, const float* gamma,
-                         void* dz, void* dbranch, float* dgamma, float* dbeta, long long rows, int d, uint32_t thr,
+                         void* dz, void* dbranch, float* dgamma, float* dbeta, float* dbias, long long rows, int d, uint32_t thr,
                          float inv_keep, uint64_t seed, uint64_t site, cudaStream_t st) {
   constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
   if (d % VEC) { smer_set_error("smer_layernorm_bwd: d=%d must be a multiple of %d for this dtype", d, VEC); return SMER_ERR_ARG; }
@@ -274,13 +285,13 @@ static int ln_bwd_launch(const void* dy, const void* z, const float* mean, const
   long long cap = (long long)smer_num_sms() * 4;
   int grid = (int)(blocks < cap ? blocks : cap);
   if (grid < 1) grid = 1;
-  size_t smem = 2 * 8 * (size_t)d * sizeof(float);
+  size_t smem = 3 * 8 * (size_t)d * sizeof(float);
 #define LN_CASE(I)                                                                                              \
   case I:                                                                                                       \
     if (smem > 48 * 1024)                                                                                       \
       cudaFuncSetAttribute(ln_bwd_kernel<T, I, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     ln_bwd_kernel<T, I, VEC><<<grid, 256, smem, st>>>((const T*)dy, (const T*)z, mean, rstd, gamma, (T*)dz, (T*)dbranch, \
-                                                 dgamma, dbeta, rows, d, thr, inv_keep, seed, site, smer_seed_dev()); \
+                                                 dgamma, dbeta, dbias, rows, d, thr, inv_keep, seed, site, smer_seed_dev()); \
     break;
   switch (iters) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
@@ -294,16 +305,16 @@ static int ln_bwd_launch(const void* dy, const void* z, const float* mean, const
 
 extern "C" int smer_layernorm_bwd(const void* dy, const void* z, const float* mean, const float* rstd,
                                   const float* gamma, void* dz, void* dbranch, float* dgamma, float* dbeta,
-                                  int dtype, long long rows, int d, float dropout_p, uint64_t seed, uint64_t site,
-                                  void* stream) {
+                                  float* dbias, int dtype, long long rows, int d, float dropout_p, uint64_t seed,
+                                  uint64_t site, void* stream) {
   SMER_CHECK_ARG(d % 4 == 0 && d > 0 && d <= 128 * LN_MAX_ITERS, "smer_layernorm_bwd: need d%%4==0 and d<=1024 (got %d)", d);
   if (rows == 0) return SMER_OK;
   uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
   float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   cudaStream_t st = (cudaStream_t)stream;
   int rc = dtype == SMER_DT_F32
-               ? ln_bwd_launch<float>(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, rows, d, thr, inv_keep, seed, site, st)
-               : ln_bwd_launch<bf16>(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, rows, d, thr, inv_keep, seed, site, st);
+               ? ln_bwd_launch<float>(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dbias, rows, d, thr, inv_keep, seed, site, st)
+               : ln_bwd_launch<bf16>(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dbias, rows, d, thr, inv_keep, seed, site, st);
   if (rc) return rc;
   SMER_CHECK_LAUNCH("smer_layernorm_bwd");
   return SMER_OK;

@@ -406,14 +406,15 @@ class _Run:
             self.tape[save_key] = (z if z is not None else branch, mean, rstd)
         return y
 
-    def _ln_bwd(self, dy, ln, site, save_key, grads, gname, has_resid=True):
+    def _ln_bwd(self, dy, ln, site, save_key, grads, gname, has_resid=True, bias_name=None):
         z, mean, rstd = self.tape.pop(save_key)
         rows = dy.shape[0]
         dz = self.new(rows, self.d)
         p = self.td if has_resid else 0.0
         dbr = self.new(rows, self.d) if p > 0.0 else None
         ops.layernorm_bwd(dy, z, mean, rstd, ln[0], dz, dbr, grads[gname + "weight"], grads[gname + "bias"],
-                          dropout_p=p, seed=self.seed, site=site)
+                          dropout_p=p, seed=self.seed, site=site,
+                          dbias=grads[bias_name] if bias_name is not None else None)   # bias grad of the branch's Linear
         return dz, (dbr if dbr is not None else dz)
 
     def _attn_fwd(self, ap: _AttnP, xq, xkv, Lq, Lk, causal, key_pad, kv_len, add_mask, site_p, key, save, weights_out=None):
@@ -450,8 +451,7 @@ class _Run:
         B, d, H, dh = self.B, self.d, self.H, self.dh
         qkv, kvbuf, o, lse = self.tape.pop(key)
         n = ap.name
-        ops.colsum(dproj, grads[n + "out_proj.bias"])
-        ops.gemm_dw(dproj, o, grads[n + "out_proj.weight"])
+        ops.gemm_dw(dproj, o, grads[n + "out_proj.weight"])         # out_proj.bias: summed inside layernorm_bwd
         do = self.new(B * Lq, d)
         ops.gemm_dx(dproj, ap.wo, do)
         dsum = torch.empty(B, H, Lq, dtype=torch.float32, device=self.dev)
@@ -498,8 +498,7 @@ class _Run:
         h = self.tape.pop(key)
         n = lp.name
         rows = df.shape[0]
-        ops.colsum(df, grads[n + "linear2.bias"])
-        ops.gemm_dw(df, h, grads[n + "linear2.weight"])
+        ops.gemm_dw(df, h, grads[n + "linear2.weight"])             # linear2.bias: summed inside layernorm_bwd
         dh = self.new(rows, self.ff)
         ops.gemm_dx(df, lp.w2, dh, resid=h, flags=K.EPI_GATE, dropout_p=self.td)
         ops.colsum(dh, grads[n + "linear1.bias"])
@@ -599,12 +598,15 @@ class _Run:
         for i in reversed(range(len(self.dec_p))):
             lp = self.dec_p[i]
             n = lp.name
-            dz3, df = self._ln_bwd(dy, lp.ln[2], _site(_KIND_DEC, i, _SUB_DROP3), f"d{i}.ln3", grads, n + "norm3.")
+            dz3, df = self._ln_bwd(dy, lp.ln[2], _site(_KIND_DEC, i, _SUB_DROP3), f"d{i}.ln3", grads, n + "norm3.",
+                                   bias_name=n + "linear2.bias")
             dy2 = self._ffn_bwd(lp, df, self.tape.pop(f"d{i}.y2"), f"d{i}.ffn", grads, dz3)
-            dz2, dc = self._ln_bwd(dy2, lp.ln[1], _site(_KIND_DEC, i, _SUB_DROP2), f"d{i}.ln2", grads, n + "norm2.")
+            dz2, dc = self._ln_bwd(dy2, lp.ln[1], _site(_KIND_DEC, i, _SUB_DROP2), f"d{i}.ln2", grads, n + "norm2.",
+                                   bias_name=n + "multihead_attn.out_proj.bias")
             dy1 = self._attn_bwd(lp.ca, dc, self.tape.pop(f"d{i}.y1"), mem, T, S, False, self.mem_pad, self.mem_len,
                                  None, _site(_KIND_DEC, i, _SUB_XATTN_P), f"d{i}.ca", grads, dz2, dmem)
-            dz1, da = self._ln_bwd(dy1, lp.ln[0], _site(_KIND_DEC, i, _SUB_DROP1), f"d{i}.ln1", grads, n + "norm1.")
+            dz1, da = self._ln_bwd(dy1, lp.ln[0], _site(_KIND_DEC, i, _SUB_DROP1), f"d{i}.ln1", grads, n + "norm1.",
+                                   bias_name=n + "self_attn.out_proj.bias")
             dy = self._attn_bwd(lp.sa, da, self.tape.pop(f"d{i}.y"), None, T, T, self.causal, self.tgt_pad,
                                 self.tgt_len, self.add_mask, _site(_KIND_DEC, i, _SUB_ATTN_P), f"d{i}.sa", grads, dz1)
             if hook:
@@ -617,9 +619,11 @@ class _Run:
         for i in reversed(range(len(self.enc_p))):
             lp = self.enc_p[i]
             n = lp.name
-            dz2, df = self._ln_bwd(dx, lp.ln[1], _site(_KIND_ENC, i, _SUB_DROP2), f"e{i}.ln2", grads, n + "norm2.")
+            dz2, df = self._ln_bwd(dx, lp.ln[1], _site(_KIND_ENC, i, _SUB_DROP2), f"e{i}.ln2", grads, n + "norm2.",
+                                   bias_name=n + "linear2.bias")
             dx1 = self._ffn_bwd(lp, df, self.tape.pop(f"e{i}.x1"), f"e{i}.ffn", grads, dz2)
-            dz1, da = self._ln_bwd(dx1, lp.ln[0], _site(_KIND_ENC, i, _SUB_DROP1), f"e{i}.ln1", grads, n + "norm1.")
+            dz1, da = self._ln_bwd(dx1, lp.ln[0], _site(_KIND_ENC, i, _SUB_DROP1), f"e{i}.ln1", grads, n + "norm1.",
+                                   bias_name=n + "self_attn.out_proj.bias")
             dx = self._attn_bwd(lp.sa, da, self.tape.pop(f"e{i}.x"), None, S, S, False, self.src_pad, self.src_len,
                                 None, _site(_KIND_ENC, i, _SUB_ATTN_P), f"e{i}.sa", grads, dz1)
             if hook:

@@ -77,11 +77,11 @@ def layernorm_fwd(branch, resid, gamma, beta, z_out, y, mean, rstd, eps=1e-5, dr
                 "layernorm_fwd")
 
 
-def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dropout_p=0.0, seed=0, site=0):
+def layernorm_bwd(dy, z, mean, rstd, gamma, dz, dbranch, dgamma, dbeta, dropout_p=0.0, seed=0, site=0, dbias=None):
     with _Timed("layernorm_bwd", float(dy.numel() * dy.element_size() * (3 + (dbranch is not None))), 1):
         rows, d = dy.shape
         K.check(K.lib().smer_layernorm_bwd(_p(dy), _p(z), _p(mean), _p(rstd), _p(gamma), _p(dz), _p(dbranch),
-                                           _p(dgamma), _p(dbeta), K.dt(dy), rows, d, dropout_p, seed, site, K.stream()),
+                                           _p(dgamma), _p(dbeta), _p(dbias), K.dt(dy), rows, d, dropout_p, seed, site, K.stream()),
                 "layernorm_bwd")
 
 

@@ -133,8 +133,10 @@ def test_layernorm(dev, dtype, rows, d):
     dz = torch.empty_like(br)
     dg = torch.zeros(d, device=dev)
     db = torch.zeros(d, device=dev)
-    ops.layernorm_bwd(dy, z, mean, rstd, gam, dz, None, dg, db)
+    dbias = torch.zeros(d, device=dev)
+    ops.layernorm_bwd(dy, z, mean, rstd, gam, dz, None, dg, db, dbias=dbias)
     assert rel(dz, zr.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+    assert rel(dbias, zr.grad.sum(0)) < (1e-4 if dtype == torch.float32 else 2e-2) or zr.grad.sum(0).abs().max() < 1e-3
     assert rel(dg, gr.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
     assert rel(db, br_.grad) < 1e-4
 
