@@ -134,7 +134,7 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
 // dbias (optional) += column sums of d_branch: the bias gradient of the nn.Linear that produced
 // the branch (out_proj / linear2), so no separate pass over d_branch is needed for it.
 template <typename T, int ITERS, int VEC>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dz,
               T* __restrict__ dbranch, float* __restrict__ dgamma, float* __restrict__ dbeta,
