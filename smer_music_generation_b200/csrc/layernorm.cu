@@ -9,6 +9,21 @@
 constexpr int LN_MAX_ITERS = 8;   // d <= 8 * 128 = 1024
 
 // VEC consecutive elements per lane per iteration: 4 for fp32 (16-byte accesses), 8 for bf16 (16 bytes)
+// raw 16-byte row chunks (8 bf16 or 4 fp32): loaded one row ahead of the arithmetic
+__device__ __forceinline__ uint4 ld_raw16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void cvt_raw(const uint4& t, float (&v)[8]) {        // bf16 x 8
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void cvt_raw(const uint4& t, float (&v)[4]) {        // fp32 x 4
+  v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+}
+
 template <int VEC> struct VecIO;
 template <> struct VecIO<4> {
   template <typename T> static __device__ __forceinline__ void ld(const T* p, float (&v)[4]) { load4(p, v); }
@@ -54,7 +69,7 @@ template <> struct VecIO<8> {
 };
 
 template <typename T, int ITERS, int VEC>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const float* __restrict__ gamma,
               const float* __restrict__ beta, T* __restrict__ z_out, T* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, long long rows, int d, float eps, uint32_t thr, float inv_keep,
@@ -64,7 +79,32 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   int d4 = d / VEC;
+  // software pipeline: the 16-byte chunks of row r + nwarps are in flight while row r is reduced,
+  // normalised and stored (one warp would otherwise alternate between "all loads" and "no loads")
+  uint4 rb[ITERS], rr[ITERS];
+  if (warp < rows) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      int c4 = lane + it * 32;
+      if (c4 < d4) {
+        rb[it] = ld_raw16(branch + warp * d + c4 * VEC);
+        if (resid) rr[it] = ld_raw16(resid + warp * d + c4 * VEC);
+      }
+    }
+  }
   for (long long row = warp; row < rows; row += nwarps) {
+    uint4 nb[ITERS], nr[ITERS];
+    const long long nxt = row + nwarps;
+    if (nxt < rows) {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        int c4 = lane + it * 32;
+        if (c4 < d4) {
+          nb[it] = ld_raw16(branch + nxt * d + c4 * VEC);
+          if (resid) nr[it] = ld_raw16(resid + nxt * d + c4 * VEC);
+        }
+      }
+    }
     float v[ITERS][VEC];
     float s = 0.f;
 #pragma unroll
@@ -72,7 +112,7 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
       int c4 = lane + it * 32;
       if (c4 < d4) {
         long long off = row * d + c4 * VEC;
-        VecIO<VEC>::ld(branch + off, v[it]);
+        cvt_raw(rb[it], v[it]);
         if (thr) {
           float m[VEC];
           VecIO<VEC>::drop(seed, site, (uint64_t)(row * d4 + c4), thr, inv_keep, m);
@@ -81,7 +121,7 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
         }
         if (resid) {
           float r[VEC];
-          VecIO<VEC>::ld(resid + off, r);
+          cvt_raw(rr[it], r);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) v[it][k] += r[k];
         }
@@ -95,6 +135,11 @@ ln_fwd_kernel(const T* __restrict__ branch, const T* __restrict__ resid, const f
 #pragma unroll
         for (int k = 0; k < VEC; ++k) s += v[it][k];
       }
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      rb[it] = nb[it];
+      rr[it] = nr[it];
     }
     float mu = warp_sum(s) / d;
     float q = 0.f;

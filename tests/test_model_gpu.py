@@ -213,3 +213,38 @@ def test_sampled_decode_distribution(oracle):
     chi2 = (((cnt[big] - q[big] * n) ** 2) / (q[big] * n)).sum() + (cnt[~big].sum() - q[~big].sum() * n) ** 2 / max(q[~big].sum() * n, 1e-9)
     dof = int(big.sum())
     assert chi2 / dof < 1.35, (chi2, dof)
+
+
+def test_sampled_decode_stream_statistics(oracle):
+    """Whole sampled infilling runs (multinomial, rejection loop, span bookkeeping, catch-up feeds):
+    the distribution of generated-token counts and stream lengths over many replicas matches the
+    oracle's restatement of generation_all run with numpy sampling."""
+    from smer_music_generation_b200 import InfillDecoder
+    O = oracle
+    sd = O.random_state_dict(32, 2, 1, 1, 64, 256, seed=4)
+    cfg = dict(d=32, h=2, le=1, ld=1, ff=64, maxlen=256)
+    m = _build(cfg, sd, "fp32").eval()
+    piece = O.mask_bar_and_track_ids(O.synth_piece(seed=1, n_bars=2, n_tracks=3, events_per_track_bar=2), [1, 2], [0], 3)
+    targets = O.mask_targets(1, [1, 2], 3)
+    n = 512
+    dec = InfillDecoder(m, mode="multinomial", max_len=256, seed=11, use_graph=True)
+    res = dec.generate([piece] * n, [targets] * n)
+    assert all(res["done"])
+    gen = np.array(res["generated"], dtype=np.float64)
+    lens = np.array([len(s) for s in res["streams"]], dtype=np.float64)
+    rng = np.random.default_rng(5)
+    ref_gen, ref_len = [], []
+    for _ in range(96):
+        tr = O.infill_decode(sd, piece, targets, 2, mode="sample", rng=rng)
+        ref_gen.append(tr.generated)
+        ref_len.append(len(tr.tokens))
+    ref_gen, ref_len = np.array(ref_gen, dtype=np.float64), np.array(ref_len, dtype=np.float64)
+    # means agree within 4 standard errors of the (smaller) oracle sample
+    se_g = ref_gen.std() / np.sqrt(len(ref_gen)) + gen.std() / np.sqrt(n)
+    se_l = ref_len.std() / np.sqrt(len(ref_len)) + lens.std() / np.sqrt(n)
+    assert abs(gen.mean() - ref_gen.mean()) < 4 * se_g + 0.5, (gen.mean(), ref_gen.mean())
+    assert abs(lens.mean() - ref_len.mean()) < 4 * se_l + 0.5, (lens.mean(), ref_len.mean())
+    # every stream obeys the grammar invariants: starts with m_0, one m_0 per span, no <eos>/structure ids inside
+    for s_ in res["streams"][:64]:
+        assert s_[0] == 2 and s_.count(2) == len(targets)
+        assert all(not (3 <= t <= 145) for t in s_)
