@@ -53,6 +53,15 @@ __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
     v[2 * k + 1] = f.y;
   }
 }
+__device__ __forceinline__ void cvt8(const uint4& t, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -219,6 +228,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int u = 0; u < 8; ++u) biasr[hh][u] = 0.f;
         if (f_bias && (!f_atomic || sp == 0) && colb < p.N) load8(p.bias + colb, biasr[hh]);
       }
+      // residual / gate operands (bf16): raw 16-byte chunks of all rounds, also issued before the wait
+      constexpr bool RAW_R = sizeof(TC) == 2;
+      uint4 rraw[RAW_R ? BN / 64 : 1][4];
+      if (RAW_R && has_r) {
+#pragma unroll
+        for (int hh = 0; hh < BN / 64; ++hh) {
+          const int colb = n0 + chalf * (BN / 2) + hh * 32 + lc;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = m0 + quarter * 32 + it * 8 + (lane >> 2);
+            if (row < p.M && colb < p.N)
+              rraw[RAW_R ? hh : 0][it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr + colb);
+          }
+        }
+      }
       ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
@@ -252,7 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int row = m0 + quarter * 32 + it * 8 + (lane >> 2);
-            if (row < p.M) load8(reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr + col, rsv[it]);
+            if (RAW_R) cvt8(rraw[RAW_R ? hh : 0][it], rsv[it]);
+            else if (row < p.M) load8(reinterpret_cast<const TC*>(p.resid) + (long long)row * p.ldr + col, rsv[it]);
           }
         }
 #pragma unroll

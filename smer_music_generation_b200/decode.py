@@ -216,19 +216,21 @@ class InfillDecoder:
         dev = m.embedding.weight.device
         n = len(pieces)
         d, H = m.d_model, m.nhead
-        S = max(len(p) for p in pieces)
-        S = (S + 7) // 8 * 8
-        src = torch.zeros(n, S, dtype=torch.int64)
-        pad = torch.ones(n, S, dtype=torch.bool)
-        for i, p in enumerate(pieces):
-            t = torch.as_tensor(np.asarray(p), dtype=torch.int64)
-            src[i, : len(t)] = t
-            pad[i, : len(t)] = False
+        lens = np.fromiter((len(p) for p in pieces), dtype=np.int64, count=n)
+        S = (int(lens.max()) + 7) // 8 * 8
+        src_np = np.zeros((n, S), dtype=np.int64)
+        flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in pieces])
+        cols = np.arange(S)[None, :] < lens[:, None]               # valid positions, row-major == concat order
+        src_np[cols] = flat
+        src = torch.from_numpy(src_np)
+        pad = torch.from_numpy(~cols)
         self.h2d_bytes = src.numel() * 8 + pad.numel()
         src = src.pin_memory().to(dev, non_blocking=True)
         pad_u8 = pad.to(torch.uint8).pin_memory().to(dev, non_blocking=True)
         self.n, self.S, self.dev = n, S, dev
-        self.src_len = torch.tensor([len(p) for p in pieces], dtype=torch.int32).to(dev)
+        self.src_len = torch.from_numpy(lens.astype(np.int32)).to(dev)
+        self._ev0 = torch.cuda.Event(enable_timing=True)
+        self._ev0.record()                                        # device work starts here (encoder)
         mem, run = _encode(m, src, pad_u8)
         self.cross = _cross_kv(m, run, mem)
         del mem, run
@@ -236,13 +238,14 @@ class InfillDecoder:
         dt = m.compute_dtype
         L = self.max_len
         self.self_kv = [torch.zeros(n, L, 2 * d, dtype=dt, device=dev) for _ in range(nl)]
-        max_spans = max(len(t) for t in targets)
-        tg = torch.zeros(n, max_spans, dtype=torch.int8)
-        for i, t in enumerate(targets):
-            tg[i, : len(t)] = torch.tensor([TARGET_CODES[c] for c in t], dtype=torch.int8)
+        nsp = np.fromiter((len(t) for t in targets), dtype=np.int64, count=n)
+        max_spans = int(nsp.max())
+        tg_np = np.zeros((n, max_spans), dtype=np.int8)
+        codes = np.fromiter((TARGET_CODES[c] for t in targets for c in t), dtype=np.int8, count=int(nsp.sum()))
+        tg_np[np.arange(max_spans)[None, :] < nsp[:, None]] = codes
         self.max_spans = max_spans
-        self.targets = tg.to(dev)
-        self.n_spans = torch.tensor([len(t) for t in targets], dtype=torch.int32).to(dev)
+        self.targets = torch.from_numpy(tg_np).to(dev)
+        self.n_spans = torch.from_numpy(nsp.astype(np.int32)).to(dev)
         self.nwd = torch.tensor([1 if x else 0 for x in nwd], dtype=torch.uint8).to(dev)
         self.tok_buf = torch.zeros(n, L, dtype=torch.int64, device=dev)
         self.tok_buf[:, 0] = 2                                     # every stream opens with m_0
@@ -402,9 +405,14 @@ class InfillDecoder:
                 break
         self.steps_run = steps
         self.kernel_launches = steps * self.launches_per_step
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        ev1.synchronize()
+        self.device_ms = self._ev0.elapsed_time(ev1)              # encoder + cross K/V + decode loop on the device
         tok = self.tok_buf.cpu()
         lens = self.cur_len.cpu()
         gen = self.gen_count.cpu()
         self.d2h_bytes = tok.numel() * 8 + lens.numel() * 4 + gen.numel() * 4
         streams = [tok[i, : int(lens[i])].tolist() for i in range(n)]
-        return {"streams": streams, "generated": gen.tolist(), "steps": steps, "done": self.done.cpu().tolist()}
+        return {"streams": streams, "generated": gen.tolist(), "steps": steps, "done": self.done.cpu().tolist(),
+                "device_ms": self.device_ms}

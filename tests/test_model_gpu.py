@@ -244,7 +244,8 @@ def test_sampled_decode_stream_statistics(oracle):
     se_l = ref_len.std() / np.sqrt(len(ref_len)) + lens.std() / np.sqrt(n)
     assert abs(gen.mean() - ref_gen.mean()) < 4 * se_g + 0.5, (gen.mean(), ref_gen.mean())
     assert abs(lens.mean() - ref_len.mean()) < 4 * se_l + 0.5, (lens.mean(), ref_len.mean())
-    # every stream obeys the grammar invariants: starts with m_0, one m_0 per span, no <eos>/structure ids inside
+    # grammar invariants: starts with m_0, at least one m_0 per span (m_0 itself stays sample-able,
+    # SURVEY appendix A), never a structure / time-signature / tempo / program id (generation.py:82-84)
     for s_ in res["streams"][:64]:
-        assert s_[0] == 2 and s_.count(2) == len(targets)
+        assert s_[0] == 2 and s_.count(2) >= len(targets)
         assert all(not (3 <= t <= 145) for t in s_)
