@@ -164,8 +164,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t sP_row = ptx::smem_u32(sP) + hf * (TILE_P / 2) + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
-    const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
-    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
+    const int ii = row_ok ? i : p.Lq - 1;
+    const long long rowid = ((long long)b * p.H + h) * p.Lq + ii;
+    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 1)) : 0u;
+    const uint32_t pm = (ii & 1) ? ATTN_A2 : 1u, pa = (ii & 1) ? ATTN_C2 : 0u;     // odd row of the pair: two steps ahead
     const float c2 = p.c_log2;
     float m = -INFINITY, l = 0.f;               // l: this thread's half of the row sum
     float acc[32];
@@ -245,9 +247,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (p.thr16) {
 #pragma unroll
           for (int k2 = 0; k2 < 8; ++k2) {
-            const uint32_t x = attn_pair_x(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2);
+            const uint32_t x = attn_pair_x(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2) * pm + pa;
             pv[2 * k2] = x >= p.thr16 ? pv[2 * k2] : 0.f;
-            pv[2 * k2 + 1] = attn_odd(x) >= p.thr16 ? pv[2 * k2 + 1] : 0.f;
+            pv[2 * k2 + 1] = attn_step(x) >= p.thr16 ? pv[2 * k2 + 1] : 0.f;
           }
         }
 #pragma unroll
@@ -459,8 +461,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t row_addr = ptx::smem_u32(sdS) + r * 128;
     const uint32_t rx = (uint32_t)(r & 7);
-    const long long rowid = ((long long)b * p.H + h) * p.Lq + (row_ok ? i : p.Lq - 1);
-    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid) : 0u;
+    const int ii = row_ok ? i : p.Lq - 1;
+    const long long rowid = ((long long)b * p.H + h) * p.Lq + ii;
+    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 1)) : 0u;
+    const uint32_t pm = (ii & 1) ? ATTN_A2 : 1u, pa = (ii & 1) ? ATTN_C2 : 0u;     // odd row of the pair: two steps ahead
     float lse2 = INFINITY, dsum = 0.f;
     if (row_ok) {
       const float l = p.lse[rowid];
@@ -511,9 +515,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
             float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
             if (p.thr16) {
-              const uint32_t x = attn_pair_x(rowkey, j0 + cb + k);
+              const uint32_t x = attn_pair_x(rowkey, j0 + cb + k) * pm + pa;
               d0 = x >= p.thr16 ? d0 : 0.f;
-              d1 = attn_odd(x) >= p.thr16 ? d1 : 0.f;
+              d1 = attn_step(x) >= p.thr16 ? d1 : 0.f;
             }
             // dS = P * (dP * keep/(1-p) - D)
             unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
@@ -659,6 +663,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t rx = (uint32_t)(r & 7);
     const long long rowbase = ((long long)b * p.H + h) * p.Lq;
     const float c2 = p.c_log2;
+    const uint32_t jm = (j & 1) ? ATTN_A : 1u, ja = (j & 1) ? ATTN_C : 0u;        // odd key of the pair: one step ahead
     for (int n = 0; n < ntiles; ++n) {
       const int iq0 = (it0 + n) * BKV;
       const int slot = (n & 1) * BKV;
@@ -670,7 +675,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const float l = p.lse[rowbase + i];
           l2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
           ds_ = p.dsum[rowbase + i];
-          if (p.thr16) rk = attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + i);
+          if (p.thr16) rk = attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (i & ~1));   // key of the row PAIR
         }
         s_lse[slot + r] = l2;
         s_dsum[slot + r] = ds_;
@@ -710,7 +715,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
             float q0 = p0, q1 = p1;                       // P^T * keep (unscaled: 1/(1-p) folded into dV's final scale)
             if (p.thr16) {
-              const bool k0 = attn_keep(kk[u], j, p.thr16), k1 = attn_keep(kk[u + 1], j, p.thr16);
+              // columns (u, u+1) are the even/odd query of one row pair (tile starts are even): one mix for both
+              const uint32_t x0 = attn_pair_x(kk[u], j) * jm + ja;
+              const bool k0 = x0 >= p.thr16, k1 = attn_step2(x0) >= p.thr16;
               q0 = k0 ? p0 : 0.f; q1 = k1 ? p1 : 0.f;
               d0 = k0 ? d0 : 0.f; d1 = k1 ? d1 : 0.f;
             }

@@ -174,19 +174,26 @@ __device__ __forceinline__ uint32_t attn_row_key(uint64_t seed, uint64_t site, l
   a = lowbias32(a + (uint32_t)((unsigned long long)rowid >> 32) + 0x632BE5ABu);
   return a;
 }
-// One 32-bit word per PAIR of keys: two xorshift-multiply rounds of (rowkey + pair * golden
-// ratio) give the even key's uniform; the odd key's is one more multiply-add of it.  The keep test
-// compares the full 32-bit word with thr32 = p * 2^32 (no field extraction).  ALU-pipe cost is
-// what bounds the tcgen05 attention kernels (ncu: ALU 62 %), hence the frugality.
+// One 32-bit word per 2x2 BLOCK of (query row pair, key pair): two xorshift-multiply rounds of
+// (pair-row key + key-pair index * golden ratio).  Element (i & 1, j & 1) of the block uses that
+// word advanced by 2*(i&1) + (j&1) multiply-add steps; keep iff word >= thr32 = p * 2^32 (full
+// word compare, no field extraction).  Kernels that walk along keys (forward, dQ) share the mix
+// across a key pair, the dK/dV kernel (one thread per key, walking along queries) shares it
+// across a query pair -- instruction issue is what bounds the tcgen05 attention kernels.
+// The row key is taken for the EVEN row of the pair: attn_row_key(seed, site, rowbase + (i & ~1)).
+constexpr uint32_t ATTN_A = 0x297A2D39u, ATTN_C = 0x7F4A7C15u;
+constexpr uint32_t ATTN_A2 = ATTN_A * ATTN_A, ATTN_C2 = (ATTN_A + 1u) * ATTN_C;     // two steps at once
 __device__ __forceinline__ uint32_t attn_pair_x(uint32_t rowkey, int j) {
   uint32_t x = rowkey + (uint32_t)(j >> 1) * 0x9E3779B9u;
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u;
   return x;
 }
-__device__ __forceinline__ uint32_t attn_odd(uint32_t x) { return x * 0x297A2D39u + 0x7F4A7C15u; }
-__device__ __forceinline__ bool attn_keep(uint32_t rowkey, int j, uint32_t thr32) {
-  uint32_t x = attn_pair_x(rowkey, j);
-  if (j & 1) x = attn_odd(x);
+__device__ __forceinline__ uint32_t attn_step(uint32_t x) { return x * ATTN_A + ATTN_C; }
+__device__ __forceinline__ uint32_t attn_step2(uint32_t x) { return x * ATTN_A2 + ATTN_C2; }
+__device__ __forceinline__ bool attn_keep(uint32_t pairkey, int i_parity, int j, uint32_t thr32) {
+  uint32_t x = attn_pair_x(pairkey, j);
+  if (i_parity & 1) x = attn_step2(x);
+  if (j & 1) x = attn_step(x);
   return x >= thr32;
 }
 
