@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/smer_b200.h"
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -31,9 +32,13 @@ constexpr int STAGE_EPI = 32 * 32 * 4;                        // per epilogue wa
 // Tile width BN is 256 when the problem has enough 128x256 tiles to fill the GPU (each A byte
 // fetched from L2 then feeds twice the MACs -- 128x128 tiles are L2-bandwidth-bound at ~1/3 of the
 // tensor peak), else 128.  Same smem budget either way: 6 x 32 KB or 4 x 48 KB stages.
-template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr int B_BYTES = BN * BK * 2;
+// CTAS = 2: a CTA pair (cluster of two, one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 rows of A and its own BN/2 columns of B, so a stage is again 32 KB
+// (6 stages) while every byte fetched from L2 feeds twice the MACs of the single-CTA 128 x 256 tile.
+template <int BN, int CTAS = 1> struct Cfg {
+  static constexpr int BNC = BN / CTAS;                 // B columns staged by one CTA
+  static constexpr int B_BYTES = BNC * BK * 2;
+  static constexpr int STAGES = B_BYTES > TILE_BYTES ? 4 : 6;
   static constexpr int STAGE_BYTES = TILE_BYTES + B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGE_EPI + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -99,16 +104,18 @@ struct EpiParams {
 // (the per-element flag branches and dead operand loads were ~1/3 of the epilogue's instructions).
 enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RELU_DROP = 3, EPI_RESID = 4, EPI_GATE = 5, EPI_ATOMIC = 6 };
 
-template <bool A_MN, bool B_MN, typename TC, int BN, int EPI>
+template <bool A_MN, bool B_MN, typename TC, int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int STAGES = Cfg<BN>::STAGES;
-  constexpr int B_BYTES = Cfg<BN>::B_BYTES;
+  using C = Cfg<BN, CTAS>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int B_BYTES = C::B_BYTES;
+  constexpr int BNC = C::BNC;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TILE_BYTES;
-  uint8_t* sEpi = smem + STAGES * Cfg<BN>::STAGE_BYTES;
+  uint8_t* sEpi = smem + STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi + EPI_WARPS * STAGE_EPI);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
@@ -118,6 +125,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int total = tiles_mn * p.splits;
+  const int rank = CTAS == 2 ? (int)ptx::cluster_ctarank() : 0;     // 0 = leader (issues the MMAs of the pair)
+  const int cid = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // work-list position of this CTA / pair
+  const int nworkers = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -128,52 +138,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full_bar + a, 1);
-      ptx::mbar_init(tmem_empty_bar + a, EPI_WARPS);
+      ptx::mbar_init(tmem_empty_bar + a, EPI_WARPS * CTAS);      // (leader's) drained by the epilogue warps of every CTA
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<Cfg<BN>::TMEM_COLS>(tmem_ptr);
+  if (warp == 1) {
+    if (CTAS == 2) ptx::tmem_alloc_2sm<C::TMEM_COLS>(tmem_ptr);
+    else ptx::tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync();            // the peer's barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     if (ptx::elect_one()) {
       int it = 0;                                            // global k-block counter -> ring slot / parity
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      auto tma = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+        if (CTAS == 2) ptx::tma_load_2d_2sm(dst, m, bar, c0, c1);       // completes on the leader's barrier
+        else ptx::tma_load_2d(dst, m, bar, c0, c1);
+      };
+      for (int w = cid; w < total; w += nworkers) {
         const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
-        const int m0 = (rem / p.tiles_n) * BM, n0 = (rem % p.tiles_n) * BN;
+        const int m0 = (rem / p.tiles_n) * (BM * CTAS) + rank * BM;        // this CTA's 128 rows of A
+        const int n0 = (rem % p.tiles_n) * BN + rank * BNC;                // this CTA's BN/CTAS columns of B
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);
-          ptx::mbar_expect_tx(full_bar + s, Cfg<BN>::STAGE_BYTES);
+          if (rank == 0) ptx::mbar_expect_tx(full_bar + s, CTAS * C::STAGE_BYTES);   // bytes of the whole pair
           const int k = kb * BK;
           uint8_t* a = sA + s * TILE_BYTES;
           uint8_t* b = sB + s * B_BYTES;
           if (!A_MN) {
-            ptx::tma_load_2d(a, &tmap_a, full_bar + s, k, m0);
+            tma(a, &tmap_a, full_bar + s, k, m0);
           } else {
-            ptx::tma_load_2d(a, &tmap_a, full_bar + s, m0, k);
-            ptx::tma_load_2d(a + TILE_BYTES / 2, &tmap_a, full_bar + s, m0 + 64, k);
+            tma(a, &tmap_a, full_bar + s, m0, k);
+            tma(a + TILE_BYTES / 2, &tmap_a, full_bar + s, m0 + 64, k);
           }
           if (!B_MN) {
-            ptx::tma_load_2d(b, &tmap_b, full_bar + s, k, n0);                 // one box: BN rows x 64 k
+            tma(b, &tmap_b, full_bar + s, k, n0);                               // one box: BNC rows x 64 k
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)                                   // 64-column chunks, 8 KB apart
-              ptx::tma_load_2d(b + c * (TILE_BYTES / 2), &tmap_b, full_bar + s, n0 + c * 64, k);
+            for (int c = 0; c < BNC / 64; ++c)                                  // 64-column chunks, 8 KB apart
+              tma(b + c * (TILE_BYTES / 2), &tmap_b, full_bar + s, n0 + c * 64, k);
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * CTAS, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int it = 0, item = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++item) {
+      for (int w = cid; w < total; w += nworkers, ++item) {
         const int sp = w / tiles_mn;
         const int kb0 = sp * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int acc = item & 1;
@@ -192,11 +211,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // MN-major: 16 k-rows = 2048 B; 64-element MN chunks are 8192 B apart, 8-row groups 1024 B.
             const uint64_t ad = A_MN ? ptx::make_smem_desc(a + k * 2048, 8192, 1024) : ptx::make_smem_desc(a + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? ptx::make_smem_desc(b + k * 2048, 8192, 1024) : ptx::make_smem_desc(b + k * 32, 16, 1024);
-            ptx::umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTAS == 2) ptx::umma_bf16_ss_2sm(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(empty_bar + s);        // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CTAS == 2) ptx::umma_commit_2sm(empty_bar + s); else ptx::umma_commit(empty_bar + s);
         }
-        ptx::umma_commit(tmem_full_bar + acc);    // accumulator complete
+        // accumulator complete (signalled to the epilogue warps of both CTAs of a pair)
+        if (CTAS == 2) ptx::umma_commit_2sm(tmem_full_bar + acc); else ptx::umma_commit(tmem_full_bar + acc);
       }
     }
     __syncwarp();
@@ -214,9 +236,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int chalf = (warp - 2) >> 2;              // which 64 of the tile's 128 columns
     const uint32_t stage_addr = ptx::smem_u32(sEpi + (warp - 2) * STAGE_EPI);
     int item = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++item) {
+    for (int w = cid; w < total; w += nworkers, ++item) {
       const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
-      const int m0 = (rem / p.tiles_n) * BM, n0 = (rem % p.tiles_n) * BN;
+      const int m0 = (rem / p.tiles_n) * (BM * CTAS) + rank * BM, n0 = (rem % p.tiles_n) * BN;
       const int acc = item & 1;
       // bias of this warp's columns: issued before the accumulator wait so its latency is hidden
       const int lc = (lane & 3) * 8;
@@ -257,7 +279,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (hh == BN / 64 - 1) {                               // whole accumulator part is in registers/smem
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + acc);
+          if (lane == 0) {
+            if (CTAS == 2) ptx::mbar_arrive_leader(tmem_empty_bar + acc);   // the MMA issuer lives in the leader CTA
+            else ptx::mbar_arrive(tmem_empty_bar + acc);
+          }
         }
         __syncwarp();                                          // previous round's staging reads are done
         {
@@ -341,7 +366,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<Cfg<BN>::TMEM_COLS>(tmem_base);
+  if (CTAS == 2) ptx::cluster_sync();            // the leader's MMAs read the peer's smem until the very end
+  if (warp == 1) {
+    if (CTAS == 2) ptx::tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+    else ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -421,14 +450,31 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
   return SMER_OK;
 }
 
-template <bool A_MN, bool B_MN, typename TC, int BN, int EPI>
+template <bool A_MN, bool B_MN, typename TC, int BN, int EPI, int CTAS = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, TC, BN, EPI, CTAS>;
   if (!attr_set) {
-    SMER_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, TC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    SMER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CTAS>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_tc_kernel<A_MN, B_MN, TC, BN, EPI><<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  if (CTAS == 1) {
+    kern<<<grid, GEMM_THREADS, Cfg<BN, CTAS>::SMEM_BYTES, st>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;                       // 2 x number of CTA pairs
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN, CTAS>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SMER_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  }
   return SMER_OK;
 }
 
@@ -452,13 +498,16 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   const int kb_per_split = (num_kb + split_k - 1) / split_k;
   split_k = (num_kb + kb_per_split - 1) / kb_per_split;             // no empty splits
   const int tiles_m = (M + BM - 1) / BM;
-  // 128x256 tiles when they still fill the GPU (and N is wide enough to use them)
+  // 128x256 tiles when they still fill the GPU (and N is wide enough to use them); CTA pairs
+  // (256x256 tiles, cta_group::2) when there are enough of those for every pair of SMs
+  static const bool allow_2sm = [] { const char* e = getenv("SMER_GEMM_2SM"); return !(e && e[0] == '0'); }();
   const bool wide = N >= 256 && (long long)tiles_m * ((N + 255) / 256) * split_k >= sms;
+  const bool pair = allow_2sm && wide && (long long)((M + 255) / 256) * ((N + 255) / 256) * split_k >= sms / 2;
   const int bn = wide ? 256 : 128;
   if (a_kmajor) rc = smer_make_tmap_bf16(&ta, A, K, M, lda, BK, BM);
   else rc = smer_make_tmap_bf16(&ta, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (b_kmajor) rc = smer_make_tmap_bf16(&tb, B, K, N, ldb, BK, bn);
+  if (b_kmajor) rc = smer_make_tmap_bf16(&tb, B, K, N, ldb, BK, pair ? bn / 2 : bn);      // a CTA of a pair stages half of B
   else rc = smer_make_tmap_bf16(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   EpiParams p;
@@ -469,10 +518,11 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   p.num_kb = num_kb;
   p.kb_per_split = kb_per_split;
   p.tiles_n = (N + bn - 1) / bn;
-  p.tiles_m = tiles_m;
+  p.tiles_m = pair ? (M + 2 * BM - 1) / (2 * BM) : tiles_m;
   p.splits = split_k;
   const long long total = (long long)p.tiles_n * p.tiles_m * split_k;
-  dim3 grid((unsigned)(total < sms ? total : sms));
+  const long long workers = pair ? sms / 2 : sms;
+  dim3 grid((unsigned)((total < workers ? total : workers) * (pair ? 2 : 1)));
   cudaStream_t st = (cudaStream_t)stream;
   const bool amn = !a_kmajor, bmn = !b_kmajor, f32 = out_dtype == SMER_DT_F32;
   // epilogue variant: the specialised ones cover the shapes the transformer stack launches
@@ -482,7 +532,9 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   else if (flags == 0 && resid && !bias && !p.thr) epi = EPI_RESID;
   else if (flags == SMER_EPI_RELU && bias && !resid) epi = p.thr ? EPI_BIAS_RELU_DROP : EPI_BIAS_RELU;
   else if (flags == 0 && bias && !resid && !p.thr) epi = EPI_BIAS;
-#define GO3(AM, BMN, T, E) (wide ? launch_gemm<AM, BMN, T, 256, E>(ta, tb, p, grid, st) : launch_gemm<AM, BMN, T, 128, E>(ta, tb, p, grid, st))
+#define GO3(AM, BMN, T, E)                                                                          \
+  (pair ? launch_gemm<AM, BMN, T, 256, E, 2>(ta, tb, p, grid, st)                                   \
+        : wide ? launch_gemm<AM, BMN, T, 256, E>(ta, tb, p, grid, st) : launch_gemm<AM, BMN, T, 128, E>(ta, tb, p, grid, st))
   if (!amn && !bmn) {                       // nn.Linear forward
     if (f32) rc = epi == EPI_BIAS ? GO3(false, false, float, EPI_BIAS) : GO3(false, false, float, EPI_GENERIC);
     else if (epi == EPI_BIAS) rc = GO3(false, false, bf16, EPI_BIAS);

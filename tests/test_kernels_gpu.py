@@ -51,6 +51,41 @@ def test_gemm_tc_nt(dev, M, N, K_):
     assert rel(out, ref + res.float()) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K_", [(8192, 1536, 512), (8292, 512, 512), (10000, 320, 512), (16384, 2048, 256)])
+def test_gemm_tc_cta_pair_shapes(dev, M, N, K_):
+    """Shapes large enough for the cta_group::2 (CTA-pair, 256x256 tile) variant: forward with every
+    specialised epilogue, input gradient (B MN-major) and split-K weight gradient (A and B MN-major)."""
+    ops, K = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    A = (torch.randn(M, K_, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(N, K_, generator=g) * 0.1).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = A.float() @ W.float().t() + bias
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ops.gemm_nt(A, W, out, bias=bias)
+    assert rel(out, ref) < 1e-2
+    ops.gemm_nt(A, W, out, bias=bias, flags=K.EPI_RELU)
+    assert rel(out, torch.relu(ref)) < 1e-2
+    out32 = torch.empty(M, N, dtype=torch.float32, device=dev)
+    ops.gemm_nt(A, W, out32, bias=bias)
+    assert rel(out32, ref) < 1e-5
+    # dropout epilogue: kept entries equal relu(ref)/(1-p), keep rate ~ 0.9
+    ops.gemm_nt(A, W, out, bias=bias, flags=K.EPI_RELU, dropout_p=0.1, seed=5, site=9)
+    pos = torch.relu(ref) > 1e-3
+    kept = (out.float() != 0) & pos
+    assert abs(kept.sum().item() / pos.sum().item() - 0.9) < 5e-3
+    assert rel(out.float()[kept], (torch.relu(ref) / 0.9)[kept]) < 1e-2
+    # input gradient and weight gradient
+    dY = (torch.randn(M, N, generator=g) * 0.3).to(dev).bfloat16()
+    res = torch.randn(M, K_, generator=g).to(dev).bfloat16()
+    dx = torch.empty(M, K_, dtype=torch.bfloat16, device=dev)
+    ops.gemm_dx(dY, W, dx, resid=res)
+    assert rel(dx, dY.float() @ W.float() + res.float()) < 1e-2
+    dw = torch.zeros(N, K_, dtype=torch.float32, device=dev)
+    ops.gemm_dw(dY, A, dw)
+    assert rel(dw, dY.float().t() @ A.float()) < 5e-5
+
+
 def test_gemm_tc_strided_views(dev):
     ops, K = _ops()
     g = torch.Generator().manual_seed(3)
