@@ -51,7 +51,7 @@ def test_gemm_tc_nt(dev, M, N, K_):
     assert rel(out, ref + res.float()) < 1e-2
 
 
-@pytest.mark.parametrize("M,N,K_", [(8192, 1536, 512), (8292, 512, 512), (10000, 320, 512), (16384, 2048, 256)])
+@pytest.mark.parametrize("M,N,K_", [(8192, 1536, 1024), (8292, 512, 1024), (10000, 320, 2048), (16384, 2048, 1088)])
 def test_gemm_tc_cta_pair_shapes(dev, M, N, K_):
     """Shapes large enough for the cta_group::2 (CTA-pair, 256x256 tile) variant: forward with every
     specialised epilogue, input gradient (B MN-major) and split-K weight gradient (A and B MN-major)."""
