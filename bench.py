@@ -297,6 +297,48 @@ def run_train(args):
                   {"gbs": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1)} if v["work"] else {})}
            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
+    # ---- the unchanged-train.py call pattern: module forward, SmerLoss, loss.backward(), FusedAdam.step() ----
+    module_api = None
+    if world == 1 and not args.no_module_api:
+        from smer_music_generation_b200 import SmerLoss
+        from smer_music_generation_b200.trainer import FusedAdam
+        torch.manual_seed(7)
+        m2 = ScoreTransformer(CFG["vocab"], CFG["d"], CFG["nhead"], CFG["le"], CFG["ld"], CFG["ff"], CFG["max_len"], 0.1, 0.1,
+                              compute_dtype=args.dtype).to(dev)
+        for p_ in m2.parameters():
+            if p_.dim() > 1:
+                torch.nn.init.xavier_normal_(p_)
+        m2.train()
+        crit = SmerLoss(CFG["vocab"], 0.8).to(dev)
+        opt = FusedAdam(m2.parameters(), lr=1e-4)
+        nsteps = 5
+
+        def module_step(b):
+            src, tin, tout, sp, tp = (t.to(dev, non_blocking=True) for t in b)
+            opt.zero_grad(set_to_none=True)
+            logits, _ = m2(src, tin, sp, tp, sp, "causal")
+            loss, parts, denom = crit(logits, tout)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for i in range(2):
+            module_step(host[i % nb])
+        torch.cuda.synchronize()
+        e0.record()
+        tk = 0
+        for i in range(nsteps):
+            l_ = module_step(host[i % nb])
+            _ = l_.item()                                # train.py reads the loss every step (train.py:788-797)
+            tk += ntok[i % nb]
+        e1.record()
+        torch.cuda.synchronize()
+        mms = e0.elapsed_time(e1)
+        module_api = {"value": tk / (mms * 1e-3), "unit": "tokens/s", "ms_per_step": mms / nsteps,
+                      "api": "ScoreTransformer.forward + SmerLoss + loss.backward() + FusedAdam.step(), eager launches, "
+                             "host batch in, loss.item() every step (the reference train loop's call pattern)"}
+        del m2, opt, crit
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -316,6 +358,7 @@ def run_train(args):
                 "clocks": clk,
                 "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 128,
                         "ms_per_step": ms2 / args.steps, "api": "TrainEngine.step_graph/step over ScoreTransformer (pinned host batch in, loss sums out, async D2H every step)"},
+                "e2e_module_api": module_api,
                 "gpu_launches": launches,
                 "roofline": roof,
                 "cpu_baseline": cpu,
@@ -426,6 +469,7 @@ def main():
     ap.add_argument("--splits", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-module-api", action="store_true")
     ap.add_argument("--d-model", type=int, default=512)
     ap.add_argument("--nhead", type=int, default=8)
     ap.add_argument("--layers", type=int, default=4)
