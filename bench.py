@@ -47,6 +47,15 @@ def peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        return t[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def train_flops(B, S, T, d=512, ff=2048, le=4, ld=4, V=309):
     """Algorithmic FLOPs of one forward; fwd+bwd = 3x."""
     enc_gemm = le * B * S * (8 * d * d + 4 * d * ff)
@@ -288,7 +297,8 @@ def run_train(args):
     else:
         ach = d["work"] / (d["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
-    roof.update({"kernel": dom, "traffic": None, "peak_source": pk["src"] + " (sustained)",
+    default_shape = (CFG["d"], CFG["le"], B, S, T) == (512, 4, 32, 1024, 1024)
+    roof.update({"kernel": dom, "traffic": ncu_traffic(dom) if default_shape else None, "peak_source": pk["src"] + " (sustained)",
                  "share_of_step": d["ms"] / tot_ms, "launches_per_step": d["launch_groups"],
                  "avg_launch_ms": d["ms"] / d["launch_groups"]})
     step_flops = 3.0 * train_flops(B, S, T, CFG['d'], CFG['ff'], CFG['le'], CFG['ld'])
@@ -430,7 +440,8 @@ def run_decode(args):
     pk = peaks()
     ach = pr["cross"]["bytes"] / (pr["cross"]["ms"] * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "decode_attn (cross-attention K/V)", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+            "frac": ach / pk["hbm"], "traffic": ncu_traffic("decode_attn (cross-attention K/V)") if n_total == 1024 and world == 1 else None,
+            "peak_source": pk["src"],
             "avg_launch_ms": pr["cross"]["ms"] / max(1, pr["cross"]["launches"]),
             "share_of_step": pr["cross"]["ms"] / pr["step_ms"], "eager_step_ms": pr["step_ms"],
             "self_attn_gbs": pr["self"]["bytes"] / (pr["self"]["ms"] * 1e-3) / 1e9}
