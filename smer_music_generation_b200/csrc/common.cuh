@@ -90,6 +90,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&a);
 }
 
+// Blackwell packed fp32 math (FFMA2 / FADD2 / FMUL2) and 3-input max (FMNMX3): the softmax threads of
+// the attention kernels and the LayerNorm kernels are instruction-issue-bound, so every halved instruction counts.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+
+// bf16x2 (one 32-bit word) <-> two fp32: the low half is element 0
+__device__ __forceinline__ f32x2 bf2_to_f2(uint32_t u) { return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)); }
+
 // ---------------------------------------------------------------------------------------
 // warp reductions
 // ---------------------------------------------------------------------------------------
