@@ -307,14 +307,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int BKV = 64;                         // second tile dimension of both backward kernels
 constexpr int TILE_HALF = BKV * DH * 2;         // 8 KB
 constexpr int BWD_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps (2 threads per TMEM lane)
-constexpr int DQ_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + TILE_QKV + 1024 + 256;
+constexpr int DQ_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + TILE_QKV + 1024 + 1536;    // + barriers, mask words, dsum exchange
 constexpr int DKV_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + 2 * TILE_QKV + 1024 + 2048;
 
 struct BwdParams {
   bf16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
   const float* lse;
-  const float* dsum;
+  float* dsum;               // [B,H,Lq] rowsum(dO o O): written by the dQ kernel, read by the dK/dV kernel
+  const bf16 *o, *dout;      // forward output and its gradient (for dsum)
+  long long ldo, lddo;
   const int* kv_len;
   const uint8_t* pad;
   int B, H, Lq, Lk;
@@ -459,7 +461,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (row_ok) {
       const float l = p.lse[rowid];
       lse2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
-      dsum = p.dsum[rowid];
+      // D_i = sum_c dO[i,c] * O[i,c]: this thread's 32 of the 64 columns (64 B of each row), then the pair's sum
+      const uint4* orow = reinterpret_cast<const uint4*>(p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH + hf * 32);
+      const uint4* grow = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + i) * p.lddo + h * DH + hf * 32);
+      f32x2 acc2 = pack2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 ov = orow[c], gv = grow[c];
+        acc2 = fma2(bf2_to_f2(ov.x), bf2_to_f2(gv.x), acc2);
+        acc2 = fma2(bf2_to_f2(ov.y), bf2_to_f2(gv.y), acc2);
+        acc2 = fma2(bf2_to_f2(ov.z), bf2_to_f2(gv.z), acc2);
+        acc2 = fma2(bf2_to_f2(ov.w), bf2_to_f2(gv.w), acc2);
+      }
+      float d0, d1;
+      unpack2(acc2, d0, d1);
+      dsum = d0 + d1;
+    }
+    {
+      float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][128]
+      xch[hf * 128 + r] = dsum;
+      bar_sync_bwd();
+      dsum += xch[(hf ^ 1) * 128 + r];
+      if (row_ok && hf == 0) p.dsum[rowid] = dsum;             // for the dK/dV kernel that follows on the stream
     }
     const float c2 = p.c_log2;
     for (int t = 0; t < ntiles; ++t) {
@@ -815,15 +838,11 @@ extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long dcols = (long long)a->H * DH;
   const long long rq = (long long)a->B * a->Lq, rk = (long long)a->B * a->Lk;
-  {
-    long long n = rq * a->H * 8;
-    attn_dsum_kernel<bf16><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const bf16*)a->o, a->ldo, (const bf16*)a->dout, a->lddo,
-                                                                         a->dsum, a->B, a->H, a->Lq);
-  }
   BwdParams p;
   p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv;
   p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
   p.lse = a->lse; p.dsum = a->dsum; p.kv_len = a->kv_len; p.pad = a->key_pad;
+  p.o = (const bf16*)a->o; p.dout = (const bf16*)a->dout; p.ldo = a->ldo; p.lddo = a->lddo;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.c_log2 = a->scale * 1.4426950408889634f; p.scale = a->scale; p.causal = a->causal;
   p.thr16 = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;      // p * 2^32 (full-word compare)

@@ -189,8 +189,9 @@ def attn_fwd(a):
 
 
 def attn_bwd(a):
-    with _Timed("attn_bwd", 2.0 * _attn_flops(a), 3):
-        if _attn_tc_ok(a) and ATTN_TC_BWD:
+    tc = _attn_tc_ok(a) and ATTN_TC_BWD
+    with _Timed("attn_bwd", 2.0 * _attn_flops(a), 2 if tc else 3):      # tc: dQ (+dsum) and dK/dV kernels
+        if tc:
             K.check(K.lib().smer_attn_bwd_tc(C.byref(a), K.stream()), "attn_bwd_tc")
         else:
             K.check(K.lib().smer_attn_bwd_simt(C.byref(a), K.stream()), "attn_bwd_simt")
