@@ -68,6 +68,7 @@ for name, flops, fn in cases:
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(2e6))      # ~1 ms head start so the launch is queued before the event fires
     e0.record()
     fn()
     e1.record()

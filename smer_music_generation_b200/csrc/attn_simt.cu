@@ -7,7 +7,7 @@
 //
 // Layout: token-major rows.  q[(b*Lq+i)*ldq + h*DH + c], same for k/v/o with their own pitches,
 // so the packed QKV projection output is consumed in place.  lse[(b*H+h)*Lq + i].
-// Dropout element (b,h,i,j): attn_keep(attn_row_key(seed, site, (b*H+h)*Lq + (i & ~1)), i & 1, j) -- common.cuh.
+// Dropout element (b,h,i,j): attn_keep(attn_row_key(seed, site, (b*H+h)*Lq + (i & ~7)), i, j) -- common.cuh.
 #include "common.cuh"
 #include "../../include/smer_b200.h"
 
@@ -49,13 +49,15 @@ __device__ __forceinline__ float row_dot(const float (&a)[DPT], const float* __r
   return s;
 }
 
-__device__ __forceinline__ void drop_lanes(const AttnParams& p, uint32_t rowkey, int ip, int j4, float (&m)[4]) {
-  uint32_t b0 = attn_pair_x(rowkey, j4 * 4), b1 = attn_pair_x(rowkey, j4 * 4 + 2);
-  if (ip & 1) { b0 = attn_step2(b0); b1 = attn_step2(b1); }
-  m[0] = b0 >= p.thr ? p.inv_keep : 0.f;
-  m[1] = attn_step(b0) >= p.thr ? p.inv_keep : 0.f;
-  m[2] = b1 >= p.thr ? p.inv_keep : 0.f;
-  m[3] = attn_step(b1) >= p.thr ? p.inv_keep : 0.f;
+// keys 4*j4 .. 4*j4+3 of one row; (pm, pa) = attn_advance(8 * (row & 7)) of that row
+__device__ __forceinline__ void drop_lanes(const AttnParams& p, uint32_t rowkey, uint32_t pm, uint32_t pa, int j4, float (&m)[4]) {
+  uint32_t x = attn_blk_x(rowkey, j4 * 4) * pm + pa;
+  if (j4 & 1) x = attn_step4(x);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    m[k] = x >= p.thr ? p.inv_keep : 0.f;
+    x = attn_step(x);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -84,7 +86,9 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
-  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ic & 1)) : 0u;
+  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ic & 7)) : 0u;
+  uint32_t pm = 1u, pa = 0u;
+  if (p.thr) attn_advance(8 * (ic & 7), pm, pa);
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
   const T* vb = (const T*)p.v + (long long)b * p.Lk * p.ldv + h * DH;
 
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
 #pragma unroll
     for (int j4 = 0; j4 < KT / 4; ++j4) {
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) drop_lanes(p, rowkey, ic, (j0 >> 2) + j4, dm);
+      if (p.thr) drop_lanes(p, rowkey, pm, pa, (j0 >> 2) + j4, dm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int jj = j4 * 4 + u;
@@ -200,7 +204,9 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
   }
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
   float lse = p.lse[rowid], dsum = p.dsum[rowid];
-  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ic & 1)) : 0u;
+  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ic & 7)) : 0u;
+  uint32_t pm = 1u, pa = 0u;
+  if (p.thr) attn_advance(8 * (ic & 7), pm, pa);
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
 #pragma unroll 2
     for (int j4 = 0; j4 < KT / 4; ++j4) {
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) drop_lanes(p, rowkey, ic, (j0 >> 2) + j4, dm);
+      if (p.thr) drop_lanes(p, rowkey, pm, pa, (j0 >> 2) + j4, dm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int jj = j4 * 4 + u;
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(AttnParams p) {
       float pr = masked ? 0.f : expf(s - Ls[ii]);
       float dmv = 1.f;
       if (p.thr)
-        dmv = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (min(i, p.Lq - 1) & ~1)), min(i, p.Lq - 1), jc, p.thr) ? p.inv_keep : 0.f;
+        dmv = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (min(i, p.Lq - 1) & ~7)), min(i, p.Lq - 1), jc, p.thr) ? p.inv_keep : 0.f;
       float dp = row_dot<DPT, TPR>(vr, &Gs[ii][part * DPT]) * dmv;
       float ds = pr * (dp - Ds[ii]);
       float pd = pr * dmv;
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_weights_kernel(AttnParams p, fl
         if (p.addmask) s += p.addmask[(long long)i * p.ldmask + j];
         long long rowid = ((long long)b * p.H + h) * p.Lq + i;
         float pr = expf(s - p.lse[rowid]);
-        if (p.thr) pr = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (i & 1)), i, j, p.thr) ? pr * p.inv_keep : 0.f;
+        if (p.thr) pr = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (i & 7)), i, j, p.thr) ? pr * p.inv_keep : 0.f;
         acc += pr;
       }
     }

@@ -156,8 +156,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t rx = (uint32_t)(r & 7);
     const int ii = row_ok ? i : p.Lq - 1;
     const long long rowid = ((long long)b * p.H + h) * p.Lq + ii;
-    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 1)) : 0u;
-    const uint32_t pm = (ii & 1) ? ATTN_A2 : 1u, pa = (ii & 1) ? ATTN_C2 : 0u;     // odd row of the pair: two steps ahead
+    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 7)) : 0u;
+    uint32_t pm = 1u, pa = 0u;                     // row (ii & 7) of the 8x8 dropout block: 8 steps per row
+    if (p.thr16) attn_advance(8 * (ii & 7), pm, pa);
     const float c2 = p.c_log2;
     float m = -INFINITY, l = 0.f;               // l: this thread's half of the row sum
     float acc[32];
@@ -198,7 +199,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (w == 0u) {
 #pragma unroll
           for (int k = 0; k < 32; k += 2) mx = max3(mx, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
-        } else {
+        } else if (w != 0xffffffffu) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) mx = fmaxf(mx, ((w >> k) & 1u) ? -INFINITY : __uint_as_float(v[k]));
         }
@@ -212,6 +213,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float alpha = ex2(m - m_use);
       f32x2 lsum2 = pack2(0.f, 0.f);
       const f32x2 c2p = pack2(c2, c2), nm2 = pack2(-m_use, -m_use);
+      const uint32_t kbase = rowkey + (uint32_t)((j0 + hf * 64) >> 3) * ATTN_GOLD;     // dropout block index of this thread's keys
       // ---- pass 2: P = exp2(S*c - m), row sum, dropout, bf16 pack into the swizzled A-operand tile
       // (dropout keeps P unscaled here: the 1/(1-p) factor is folded into the final O normalisation)
 #pragma unroll
@@ -220,6 +222,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::tmem_ld_32x16(lane_addr + hf * 64 + sc * 16, v);
         ptx::tmem_ld_wait();
         const uint32_t w = mw[sc >> 1] >> ((sc & 1) * 16);
+        if ((w & 0xFFFFu) == 0xFFFFu) {                  // nothing visible in this group: P = 0
+          st_shared_v4(sP_row + (((uint32_t)(sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
+          st_shared_v4(sP_row + (((uint32_t)(sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
+          continue;
+        }
         float pv[16];
 #pragma unroll
         for (int k = 0; k < 16; k += 2) {
@@ -236,10 +243,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         if (p.thr16) {
 #pragma unroll
-          for (int k2 = 0; k2 < 8; ++k2) {
-            const uint32_t x = attn_pair_x(rowkey, j0 + hf * 64 + sc * 16 + 2 * k2) * pm + pa;
-            pv[2 * k2] = x >= p.thr16 ? pv[2 * k2] : 0.f;
-            pv[2 * k2 + 1] = attn_step(x) >= p.thr16 ? pv[2 * k2 + 1] : 0.f;
+          for (int q8 = 0; q8 < 2; ++q8) {             // one mixed word per 8 keys, then one multiply-add per key
+            uint32_t x = attn_mix(kbase + (uint32_t)(sc * 2 + q8) * ATTN_GOLD) * pm + pa;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              pv[q8 * 8 + k] = x >= p.thr16 ? pv[q8 * 8 + k] : 0.f;
+              if (k < 7) x = attn_step(x);
+            }
           }
         }
 #pragma unroll
@@ -455,8 +465,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t rx = (uint32_t)(r & 7);
     const int ii = row_ok ? i : p.Lq - 1;
     const long long rowid = ((long long)b * p.H + h) * p.Lq + ii;
-    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 1)) : 0u;
-    const uint32_t pm = (ii & 1) ? ATTN_A2 : 1u, pa = (ii & 1) ? ATTN_C2 : 0u;     // odd row of the pair: two steps ahead
+    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 7)) : 0u;
+    uint32_t pm = 1u, pa = 0u;                     // row (ii & 7) of the 8x8 dropout block: 8 steps per row
+    if (p.thr16) attn_advance(8 * (ii & 7), pm, pa);
     float lse2 = INFINITY, dsum = 0.f;
     if (row_ok) {
       const float l = p.lse[rowid];
@@ -517,20 +528,30 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
           ptx::tmem_ld_wait();
           float ds[16];
+          const uint32_t w16 = (w >> (sc * 16)) & 0xFFFFu;
+          const uint32_t kbase = rowkey + (uint32_t)((j0 + cb) >> 3) * ATTN_GOLD;
+          uint32_t xk = 0u;
+          if (w16 == 0xFFFFu) {                          // nothing visible in this group: dS = 0
+            st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
+            st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < 16; k += 2) {
             float e0, e1;
             unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, nl2), e0, e1);
             float p0 = ex2(e0), p1 = ex2(e1);
-            if (w != 0u) {
-              p0 = ((w >> (sc * 16 + k)) & 1u) ? 0.f : p0;
-              p1 = ((w >> (sc * 16 + k + 1)) & 1u) ? 0.f : p1;
+            if (w16 != 0u) {
+              p0 = ((w16 >> k) & 1u) ? 0.f : p0;
+              p1 = ((w16 >> (k + 1)) & 1u) ? 0.f : p1;
             }
             float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
             if (p.thr16) {
-              const uint32_t x = attn_pair_x(rowkey, j0 + cb + k) * pm + pa;
-              d0 = x >= p.thr16 ? d0 : 0.f;
-              d1 = attn_step(x) >= p.thr16 ? d1 : 0.f;
+              if ((k & 7) == 0) xk = attn_mix(kbase + (uint32_t)(k >> 3) * ATTN_GOLD) * pm + pa;   // new 8-key block
+              d0 = xk >= p.thr16 ? d0 : 0.f;
+              xk = attn_step(xk);
+              d1 = xk >= p.thr16 ? d1 : 0.f;
+              if ((k & 7) != 6) xk = attn_step(xk);
             }
             // dS = P * (dP * keep/(1-p) - D)
             unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
@@ -676,7 +697,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t rx = (uint32_t)(r & 7);
     const long long rowbase = ((long long)b * p.H + h) * p.Lq;
     const float c2 = p.c_log2;
-    const uint32_t jm = (j & 1) ? ATTN_A : 1u, ja = (j & 1) ? ATTN_C : 0u;        // odd key of the pair: one step ahead
+    uint32_t jm = 1u, ja = 0u;                         // key (j & 7) of the 8x8 dropout block: one step per key
+    if (p.thr16) attn_advance(j & 7, jm, ja);
+    const uint32_t jg = (uint32_t)(j >> 3) * ATTN_GOLD;
     for (int n = 0; n < ntiles; ++n) {
       const int iq0 = (it0 + n) * BKV;
       const int slot = (n & 1) * BKV;
@@ -688,7 +711,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const float l = p.lse[rowbase + i];
           l2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
           ds_ = p.dsum[rowbase + i];
-          if (p.thr16) rk = attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (i & ~1));   // key of the row PAIR
+          if (p.thr16) rk = attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (i & ~7));   // key of the 8-row block
         }
         s_lse[slot + r] = l2;
         s_dsum[slot + r] = ds_;
@@ -706,7 +729,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
         ptx::tmem_ld_wait();
         float pd[16], ds[16];
-        const f32x2 c2p = pack2(c2, c2), ik2 = pack2(p.inv_keep, p.inv_keep);
+        const f32x2 c2p = pack2(c2, c2);
+        const bool need_mask = key_masked || cm > cb;     // some of this chunk's 16 queries cannot see key j
+        uint32_t xk = 0u;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
           const int colb = cb + k4 * 4;
@@ -723,21 +748,27 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             float e0, e1;
             unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, pack2(-lv[u], -lv[u + 1])), e0, e1);
             float p0 = ex2(e0), p1 = ex2(e1);
-            if (key_masked || col < cm) p0 = 0.f;
-            if (key_masked || col + 1 < cm) p1 = 0.f;
-            float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
-            float q0 = p0, q1 = p1;                       // P^T * keep (unscaled: 1/(1-p) folded into dV's final scale)
-            if (p.thr16) {
-              // columns (u, u+1) are the even/odd query of one row pair (tile starts are even): one mix for both
-              const uint32_t x0 = attn_pair_x(kk[u], j) * jm + ja;
-              const bool k0 = x0 >= p.thr16, k1 = attn_step2(x0) >= p.thr16;
-              q0 = k0 ? p0 : 0.f; q1 = k1 ? p1 : 0.f;
-              d0 = k0 ? d0 : 0.f; d1 = k1 ? d1 : 0.f;
+            if (need_mask) {
+              if (key_masked || col < cm) p0 = 0.f;
+              if (key_masked || col + 1 < cm) p1 = 0.f;
             }
-            pd[k] = q0;
-            pd[k + 1] = q1;
-            // dS^T = P * (dP * keep/(1-p) - D)
-            unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
+            const f32x2 pp = pack2(p0, p1);
+            const f32x2 dd2 = pack2(__uint_as_float(dv[k]), __uint_as_float(dv[k + 1]));
+            if (p.thr16) {
+              // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is
+              // 8 steps on.  kf = keep/(1-p): one select per element serves both P^T*kf (dV operand) and dP*kf.
+              if ((k & 7) == 0) xk = attn_mix(kk[u] + jg) * jm + ja;
+              const uint32_t x0 = xk, x1 = attn_step8(xk);
+              if ((k & 7) != 6) xk = attn_step8(x1);
+              const f32x2 kf = pack2(x0 >= p.thr16 ? p.inv_keep : 0.f, x1 >= p.thr16 ? p.inv_keep : 0.f);
+              unpack2(mul2(pp, kf), pd[k], pd[k + 1]);
+              // dS^T = P * (dP * keep/(1-p) - D)
+              unpack2(mul2(pp, fma2(dd2, kf, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
+            } else {
+              pd[k] = p0;
+              pd[k + 1] = p1;
+              unpack2(mul2(pp, add2(dd2, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
+            }
           }
         }
 #pragma unroll
@@ -757,7 +788,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
     for (int part = 0; part < 2; ++part) {           // 0: dK (scaled), 1: dV; this thread's 32 columns
       bf16* drow = (part == 0 ? p.dk + ((long long)b * p.Lk + j) * p.lddk : p.dv + ((long long)b * p.Lk + j) * p.lddv) + h * DH + hf * 32;
-      const float sc = part == 0 ? p.scale : p.inv_keep;      // dV: dropout's 1/(1-p) applied once here
+      const float sc = part == 0 ? p.scale : 1.f;             // dV's operand P^T already carries keep/(1-p)
       uint32_t v[32];
       if (ntiles > 0) {
         ptx::tmem_ld_32x32(lane_addr + 128 + part * 64 + hf * 32, v);

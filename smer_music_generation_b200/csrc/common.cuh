@@ -187,27 +187,43 @@ __device__ __forceinline__ uint32_t attn_row_key(uint64_t seed, uint64_t site, l
   a = lowbias32(a + (uint32_t)((unsigned long long)rowid >> 32) + 0x632BE5ABu);
   return a;
 }
-// One 32-bit word per 2x2 BLOCK of (query row pair, key pair): two xorshift-multiply rounds of
-// (pair-row key + key-pair index * golden ratio).  Element (i & 1, j & 1) of the block uses that
-// word advanced by 2*(i&1) + (j&1) multiply-add steps; keep iff word >= thr32 = p * 2^32 (full
-// word compare, no field extraction).  Kernels that walk along keys (forward, dQ) share the mix
-// across a key pair, the dK/dV kernel (one thread per key, walking along queries) shares it
-// across a query pair -- instruction issue is what bounds the tcgen05 attention kernels.
-// The row key is taken for the EVEN row of the pair: attn_row_key(seed, site, rowbase + (i & ~1)).
+// One 32-bit word per 8x8 BLOCK of (8 query rows, 8 keys): two xorshift-multiply rounds of
+// (block-row key + key-block index * golden ratio).  Element (i & 7, j & 7) of the block uses
+// that word advanced by 8*(i&7) + (j&7) multiply-add (LCG) steps; keep iff word >= thr32 =
+// p * 2^32 (full word compare, no field extraction).  Kernels that walk along keys (forward,
+// dQ) pay the mix once per 8 keys and one multiply-add per further key; the dK/dV kernel (one
+// thread per key, walking along queries) pays it once per 8 queries and steps by 8 at a time --
+// instruction issue on the ALU pipe is what bounds the tcgen05 attention kernels, and the
+// multiply-adds run on the FMA pipe.  The row key is taken for the FIRST row of the block:
+// attn_row_key(seed, site, rowbase + (i & ~7)).  (Offline check of the scheme: keep rate,
+// lag correlations up to 16x16 and 8x8 block-sum variance all at the binomial values.)
+constexpr int ATTN_BLK = 8;
+constexpr uint32_t ATTN_GOLD = 0x9E3779B9u;
 constexpr uint32_t ATTN_A = 0x297A2D39u, ATTN_C = 0x7F4A7C15u;
-constexpr uint32_t ATTN_A2 = ATTN_A * ATTN_A, ATTN_C2 = (ATTN_A + 1u) * ATTN_C;     // two steps at once
-__device__ __forceinline__ uint32_t attn_pair_x(uint32_t rowkey, int j) {
-  uint32_t x = rowkey + (uint32_t)(j >> 1) * 0x9E3779B9u;
+constexpr uint32_t lcg_mul_n(int n) { uint32_t m = 1u; for (int i = 0; i < n; ++i) m *= ATTN_A; return m; }
+constexpr uint32_t lcg_add_n(int n) { uint32_t a = 0u; for (int i = 0; i < n; ++i) a = a * ATTN_A + ATTN_C; return a; }
+constexpr uint32_t ATTN_A4 = lcg_mul_n(4), ATTN_C4 = lcg_add_n(4);                  // four steps at once
+constexpr uint32_t ATTN_A8 = lcg_mul_n(8), ATTN_C8 = lcg_add_n(8);                  // eight steps: next row of a block
+__device__ __forceinline__ uint32_t attn_mix(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u;
   return x;
 }
+__device__ __forceinline__ uint32_t attn_blk_x(uint32_t blockkey, int j) {
+  return attn_mix(blockkey + (uint32_t)(j >> 3) * ATTN_GOLD);
+}
 __device__ __forceinline__ uint32_t attn_step(uint32_t x) { return x * ATTN_A + ATTN_C; }
-__device__ __forceinline__ uint32_t attn_step2(uint32_t x) { return x * ATTN_A2 + ATTN_C2; }
-__device__ __forceinline__ bool attn_keep(uint32_t pairkey, int i_parity, int j, uint32_t thr32) {
-  uint32_t x = attn_pair_x(pairkey, j);
-  if (i_parity & 1) x = attn_step2(x);
-  if (j & 1) x = attn_step(x);
-  return x >= thr32;
+__device__ __forceinline__ uint32_t attn_step4(uint32_t x) { return x * ATTN_A4 + ATTN_C4; }
+__device__ __forceinline__ uint32_t attn_step8(uint32_t x) { return x * ATTN_A8 + ATTN_C8; }
+// n LCG steps as one multiply-add: x -> x * mul + add
+__device__ __forceinline__ void attn_advance(int n, uint32_t& mul, uint32_t& add) {
+  mul = 1u; add = 0u;
+  for (int k = 0; k < n; ++k) { mul *= ATTN_A; add = add * ATTN_A + ATTN_C; }
+}
+// generic (slow) form: blockkey = attn_row_key(seed, site, rowbase + (i & ~7))
+__device__ __forceinline__ bool attn_keep(uint32_t blockkey, int i, int j, uint32_t thr32) {
+  uint32_t mul, add;
+  attn_advance(8 * (i & 7) + (j & 7), mul, add);
+  return attn_blk_x(blockkey, j) * mul + add >= thr32;
 }
 
 static inline uint32_t dropout_threshold(float p) {
