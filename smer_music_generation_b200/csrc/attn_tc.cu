@@ -15,6 +15,8 @@
 //               reads; O accumulated in fp32 registers with the online-softmax rescale.
 //   Two CTAs share an SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
 //   other's MMAs.
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/smer_b200.h"
@@ -216,45 +218,53 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t kbase = rowkey + (uint32_t)((j0 + hf * 64) >> 3) * ATTN_GOLD;     // dropout block index of this thread's keys
       // ---- pass 2: P = exp2(S*c - m), row sum, dropout, bf16 pack into the swizzled A-operand tile
       // (dropout keeps P unscaled here: the 1/(1-p) factor is folded into the final O normalisation)
+      // The masked variant is a separate instantiation behind a warp-uniform branch (tcgen05.ld is warp-collective):
+      // inside one instantiation ptxas would predicate the per-score mask tests and issue them on every tile.
+      auto pass2 = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-      for (int sc = 0; sc < 4; ++sc) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(lane_addr + hf * 64 + sc * 16, v);
-        ptx::tmem_ld_wait();
-        const uint32_t w = mw[sc >> 1] >> ((sc & 1) * 16);
-        if ((w & 0xFFFFu) == 0xFFFFu) {                  // nothing visible in this group: P = 0
-          st_shared_v4(sP_row + (((uint32_t)(sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
-          st_shared_v4(sP_row + (((uint32_t)(sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
-          continue;
-        }
-        float pv[16];
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-          float s0 = __uint_as_float(v[k]), s1 = __uint_as_float(v[k + 1]);
-          if ((w & 0xFFFFu) != 0u) {
-            s0 = ((w >> k) & 1u) ? -INFINITY : s0;
-            s1 = ((w >> (k + 1)) & 1u) ? -INFINITY : s1;
+        for (int sc = 0; sc < 4; ++sc) {
+          uint32_t v[16];
+          if (MASKED) __syncwarp();                      // reconverge after the divergent skip below: tcgen05.ld is .aligned
+          ptx::tmem_ld_32x16(lane_addr + hf * 64 + sc * 16, v);
+          ptx::tmem_ld_wait();
+          const uint32_t w = MASKED ? (mw[sc >> 1] >> ((sc & 1) * 16)) & 0xFFFFu : 0u;
+          if (MASKED && w == 0xFFFFu) {                  // nothing visible in this group: P = 0
+            st_shared_v4(sP_row + (((uint32_t)(sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
+            st_shared_v4(sP_row + (((uint32_t)(sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
+            continue;
           }
-          float e0, e1;
-          unpack2(fma2(pack2(s0, s1), c2p, nm2), e0, e1);
-          pv[k] = ex2(e0);
-          pv[k + 1] = ex2(e1);
-          lsum2 = add2(lsum2, pack2(pv[k], pv[k + 1]));
-        }
-        if (p.thr16) {
+          float pv[16];
 #pragma unroll
-          for (int q8 = 0; q8 < 2; ++q8) {             // one mixed word per 8 keys, then one multiply-add per key
-            uint32_t x = attn_mix(kbase + (uint32_t)(sc * 2 + q8) * ATTN_GOLD) * pm + pa;
+          for (int k = 0; k < 16; k += 2) {
+            float s0 = __uint_as_float(v[k]), s1 = __uint_as_float(v[k + 1]);
+            if (MASKED) {
+              s0 = ((w >> k) & 1u) ? -INFINITY : s0;
+              s1 = ((w >> (k + 1)) & 1u) ? -INFINITY : s1;
+            }
+            float e0, e1;
+            unpack2(fma2(pack2(s0, s1), c2p, nm2), e0, e1);
+            pv[k] = ex2(e0);
+            pv[k + 1] = ex2(e1);
+            lsum2 = add2(lsum2, pack2(pv[k], pv[k + 1]));
+          }
+          if (p.thr16) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              pv[q8 * 8 + k] = x >= p.thr16 ? pv[q8 * 8 + k] : 0.f;
-              if (k < 7) x = attn_step(x);
+            for (int q8 = 0; q8 < 2; ++q8) {             // one mixed word per 8 keys, then one multiply-add per key
+              uint32_t x = attn_mix(kbase + (uint32_t)(sc * 2 + q8) * ATTN_GOLD) * pm + pa;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                pv[q8 * 8 + k] = x >= p.thr16 ? pv[q8 * 8 + k] : 0.f;
+                if (k < 7) x = attn_step(x);
+              }
             }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) st_row_chunk_fwd(sP_row, rx, (uint32_t)(sc * 2 + q), pv + 8 * q);
-      }
+          for (int q = 0; q < 2; ++q) st_row_chunk_fwd(sP_row, rx, (uint32_t)(sc * 2 + q), pv + 8 * q);
+        }
+      };
+      if (__any_sync(0xffffffffu, (mw[0] | mw[1]) != 0u)) pass2(std::true_type{});
+      else pass2(std::false_type{});
       {
         float ls0, ls1;
         unpack2(lsum2, ls0, ls1);
@@ -520,45 +530,52 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       {
         const uint32_t w = mw[hf];
         const f32x2 c2p = pack2(c2, c2), nl2 = pack2(-lse2, -lse2), ik2 = pack2(p.inv_keep, p.inv_keep), nd2 = pack2(-dsum, -dsum);
+        // masked tiles take a separate instantiation behind a warp-uniform branch (see the forward kernel)
+        auto chunks = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-        for (int sc = 0; sc < 2; ++sc) {               // two 16-column sub-chunks keep the register count low
-          const int cb = hf * 32 + sc * 16;
-          uint32_t sv[16], dv[16];
-          ptx::tmem_ld_32x16(lane_addr + cb, sv);
-          ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
-          ptx::tmem_ld_wait();
-          float ds[16];
-          const uint32_t w16 = (w >> (sc * 16)) & 0xFFFFu;
-          const uint32_t kbase = rowkey + (uint32_t)((j0 + cb) >> 3) * ATTN_GOLD;
-          uint32_t xk = 0u;
-          if (w16 == 0xFFFFu) {                          // nothing visible in this group: dS = 0
-            st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
-            st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
-            continue;
-          }
-#pragma unroll
-          for (int k = 0; k < 16; k += 2) {
-            float e0, e1;
-            unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, nl2), e0, e1);
-            float p0 = ex2(e0), p1 = ex2(e1);
-            if (w16 != 0u) {
-              p0 = ((w16 >> k) & 1u) ? 0.f : p0;
-              p1 = ((w16 >> (k + 1)) & 1u) ? 0.f : p1;
+          for (int sc = 0; sc < 2; ++sc) {             // two 16-column sub-chunks keep the register count low
+            const int cb = hf * 32 + sc * 16;
+            uint32_t sv[16], dv[16];
+            if (MASKED) __syncwarp();
+            ptx::tmem_ld_32x16(lane_addr + cb, sv);
+            ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
+            ptx::tmem_ld_wait();
+            float ds[16];
+            const uint32_t w16 = MASKED ? (w >> (sc * 16)) & 0xFFFFu : 0u;
+            const uint32_t kbase = rowkey + (uint32_t)((j0 + cb) >> 3) * ATTN_GOLD;
+            uint32_t xk = 0u;
+            if (MASKED && w16 == 0xFFFFu) {              // nothing visible in this group: dS = 0
+              st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
+              st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
+              continue;
             }
-            float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
-            if (p.thr16) {
-              if ((k & 7) == 0) xk = attn_mix(kbase + (uint32_t)(k >> 3) * ATTN_GOLD) * pm + pa;   // new 8-key block
-              d0 = xk >= p.thr16 ? d0 : 0.f;
-              xk = attn_step(xk);
-              d1 = xk >= p.thr16 ? d1 : 0.f;
-              if ((k & 7) != 6) xk = attn_step(xk);
-            }
-            // dS = P * (dP * keep/(1-p) - D)
-            unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
-          }
 #pragma unroll
-          for (int q = 0; q < 2; ++q) st_row_chunk(row_addr, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
-        }
+            for (int k = 0; k < 16; k += 2) {
+              float e0, e1;
+              unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, nl2), e0, e1);
+              float p0 = ex2(e0), p1 = ex2(e1);
+              if (MASKED) {
+                p0 = ((w16 >> k) & 1u) ? 0.f : p0;
+                p1 = ((w16 >> (k + 1)) & 1u) ? 0.f : p1;
+              }
+              float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
+              if (p.thr16) {
+                if ((k & 7) == 0) xk = attn_mix(kbase + (uint32_t)(k >> 3) * ATTN_GOLD) * pm + pa;   // new 8-key block
+                d0 = xk >= p.thr16 ? d0 : 0.f;
+                xk = attn_step(xk);
+                d1 = xk >= p.thr16 ? d1 : 0.f;
+                if ((k & 7) != 6) xk = attn_step(xk);
+              }
+              // dS = P * (dP * keep/(1-p) - D)
+              unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) st_row_chunk(row_addr, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
+          }
+        };
+        if (__any_sync(0xffffffffu, w != 0u)) chunks(std::true_type{});
+        else chunks(std::false_type{});
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
@@ -721,62 +738,65 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int cm = (p.causal && iq0 < j0 + BM) ? (j - iq0) : 0;       // query columns < cm cannot see key j
       ptx::mbar_wait(sp_full, n & 1);
       ptx::tc_fence_after();
+      // masked tiles (padded keys, causal diagonal) take a separate instantiation behind a warp-uniform branch
+      auto chunks = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-      for (int sc = 0; sc < 2; ++sc) {
-        const int cb = hf * 32 + sc * 16;
-        uint32_t sv[16], dv[16];
-        ptx::tmem_ld_32x16(lane_addr + cb, sv);
-        ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
-        ptx::tmem_ld_wait();
-        float pd[16], ds[16];
-        const f32x2 c2p = pack2(c2, c2);
-        const bool need_mask = key_masked || cm > cb;     // some of this chunk's 16 queries cannot see key j
-        uint32_t xk = 0u;
+        for (int sc = 0; sc < 2; ++sc) {
+          const int cb = hf * 32 + sc * 16;
+          uint32_t sv[16], dv[16];
+          ptx::tmem_ld_32x16(lane_addr + cb, sv);
+          ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
+          ptx::tmem_ld_wait();
+          float pd[16], ds[16];
+          const f32x2 c2p = pack2(c2, c2);
+          uint32_t xk = 0u;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
-          const int colb = cb + k4 * 4;
-          const float4 l4 = *reinterpret_cast<const float4*>(s_lse + slot + colb);
-          const float4 d4 = *reinterpret_cast<const float4*>(s_dsum + slot + colb);
-          const uint4 key4 = *reinterpret_cast<const uint4*>(s_key + slot + colb);
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-          const uint32_t kk[4] = {key4.x, key4.y, key4.z, key4.w};
+          for (int k4 = 0; k4 < 4; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
+            const int colb = cb + k4 * 4;
+            const float4 l4 = *reinterpret_cast<const float4*>(s_lse + slot + colb);
+            const float4 d4 = *reinterpret_cast<const float4*>(s_dsum + slot + colb);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-          for (int u = 0; u < 4; u += 2) {
-            const int k = k4 * 4 + u;
-            const int col = colb + u;
-            float e0, e1;
-            unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, pack2(-lv[u], -lv[u + 1])), e0, e1);
-            float p0 = ex2(e0), p1 = ex2(e1);
-            if (need_mask) {
-              if (key_masked || col < cm) p0 = 0.f;
-              if (key_masked || col + 1 < cm) p1 = 0.f;
-            }
-            const f32x2 pp = pack2(p0, p1);
-            const f32x2 dd2 = pack2(__uint_as_float(dv[k]), __uint_as_float(dv[k + 1]));
-            if (p.thr16) {
-              // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is
-              // 8 steps on.  kf = keep/(1-p): one select per element serves both P^T*kf (dV operand) and dP*kf.
-              if ((k & 7) == 0) xk = attn_mix(kk[u] + jg) * jm + ja;
-              const uint32_t x0 = xk, x1 = attn_step8(xk);
-              if ((k & 7) != 6) xk = attn_step8(x1);
-              const f32x2 kf = pack2(x0 >= p.thr16 ? p.inv_keep : 0.f, x1 >= p.thr16 ? p.inv_keep : 0.f);
-              unpack2(mul2(pp, kf), pd[k], pd[k + 1]);
-              // dS^T = P * (dP * keep/(1-p) - D)
-              unpack2(mul2(pp, fma2(dd2, kf, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
-            } else {
-              pd[k] = p0;
-              pd[k + 1] = p1;
-              unpack2(mul2(pp, add2(dd2, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
+            for (int u = 0; u < 4; u += 2) {
+              const int k = k4 * 4 + u;
+              const int col = colb + u;
+              float e0, e1;
+              unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, pack2(-lv[u], -lv[u + 1])), e0, e1);
+              float p0 = ex2(e0), p1 = ex2(e1);
+              if (MASKED) {
+                if (key_masked || col < cm) p0 = 0.f;
+                if (key_masked || col + 1 < cm) p1 = 0.f;
+              }
+              const f32x2 pp = pack2(p0, p1);
+              const f32x2 dd2 = pack2(__uint_as_float(dv[k]), __uint_as_float(dv[k + 1]));
+              if (p.thr16) {
+                // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is
+                // 8 steps on.  kf = keep/(1-p): one select per element serves both P^T*kf (dV operand) and dP*kf.
+                if ((k & 7) == 0) xk = attn_mix(s_key[slot + cb + k] + jg) * jm + ja;
+                const uint32_t x0 = xk, x1 = attn_step8(xk);
+                if ((k & 7) != 6) xk = attn_step8(x1);
+                const f32x2 kf = pack2(x0 >= p.thr16 ? p.inv_keep : 0.f, x1 >= p.thr16 ? p.inv_keep : 0.f);
+                unpack2(mul2(pp, kf), pd[k], pd[k + 1]);
+                // dS^T = P * (dP * keep/(1-p) - D)
+                unpack2(mul2(pp, fma2(dd2, kf, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
+              } else {
+                pd[k] = p0;
+                pd[k + 1] = p1;
+                unpack2(mul2(pp, add2(dd2, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);
+              }
             }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          st_row_chunk(pd_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), pd + 8 * q);
-          st_row_chunk(ds_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
+          for (int q = 0; q < 2; ++q) {
+            st_row_chunk(pd_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), pd + 8 * q);
+            st_row_chunk(ds_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
+          }
         }
-      }
+      };
+      if (__any_sync(0xffffffffu, key_masked || cm > hf * 32)) chunks(std::true_type{});
+      else chunks(std::false_type{});
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       ptx::mbar_arrive(pds_full);
