@@ -502,10 +502,11 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   // (256x256 tiles, cta_group::2) when there are enough of those for every pair of SMs
   static const bool allow_2sm = [] { const char* e = getenv("SMER_GEMM_2SM"); return !(e && e[0] == '0'); }();
   const bool wide = N >= 256 && (long long)tiles_m * ((N + 255) / 256) * split_k >= sms;
-  // (measured on B200: pairs win once a work item has >= 16 k-blocks -- 1024 TF vs 907 at K=2048 --
-  //  and lose a few percent at K=512, where the per-item pair synchronisation is not amortised)
+  // (measured on B200: a CTA of a pair stages half of B, one third less smem fill + operand traffic per MMA:
+  //  1243 vs 1083 TFLOP/s at K=2048, 987 vs 915-932 at K=512 with N >= 1536; the N=512, K=512 out-projection
+  //  has too few items per pair and stays on single CTAs: 700 vs 648)
   static const bool force_2sm = [] { const char* e = getenv("SMER_GEMM_2SM"); return e && e[0] == '2'; }();
-  const bool pair = allow_2sm && wide && (kb_per_split >= 16 || force_2sm) &&
+  const bool pair = allow_2sm && wide && (kb_per_split >= 16 || N >= 1024 || force_2sm) &&
                     (long long)((M + 255) / 256) * ((N + 255) / 256) * split_k >= sms / 2;
   const int bn = wide ? 256 : 128;
   if (a_kmajor) rc = smer_make_tmap_bf16(&ta, A, K, M, lda, BK, BM);
