@@ -192,18 +192,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tc_fence_after();
       // ---- pass 1: maximum of this thread's 64 visible scores, then the row maximum via smem
       float mx = -INFINITY;
+      {
+        // four chunks of 16 columns, the next one in flight while the current one is reduced
+        uint32_t v[2][16];
+        ptx::tmem_ld_32x16(lane_addr + hf * 64, v[0]);
+        ptx::tmem_ld_wait(v[0]);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(lane_addr + hf * 64 + c * 32, v);
-        ptx::tmem_ld_wait();
-        const uint32_t w = mw[c];
-        if (w == 0u) {
+        for (int c = 0; c < 4; ++c) {
+          const int cur = c & 1, nxt = cur ^ 1;
+          if (c < 3) {
+            __syncwarp();
+            ptx::tmem_ld_32x16(lane_addr + hf * 64 + (c + 1) * 16, v[nxt]);
+          }
+          const uint32_t w = (mw[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+          if (w == 0u) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 2) mx = max3(mx, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
-        } else if (w != 0xffffffffu) {
+            for (int k = 0; k < 16; k += 2) mx = max3(mx, __uint_as_float(v[cur][k]), __uint_as_float(v[cur][k + 1]));
+          } else if (w != 0xFFFFu) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, ((w >> k) & 1u) ? -INFINITY : __uint_as_float(v[k]));
+            for (int k = 0; k < 16; ++k) mx = fmaxf(mx, ((w >> k) & 1u) ? -INFINITY : __uint_as_float(v[cur][k]));
+          }
+          if (c < 3) {
+            __syncwarp();
+            ptx::tmem_ld_wait(v[nxt]);
+          }
         }
       }
       float* xch = s_xch + (t & 1) * 256;
@@ -222,45 +234,52 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // inside one instantiation ptxas would predicate the per-score mask tests and issue them on every tile.
       auto pass2 = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
+        // eight chunks of 8 columns (= one dropout block each), the next one in flight while the current is consumed
+        uint32_t v[2][8];
+        if (MASKED) __syncwarp();
+        ptx::tmem_ld_32x8(lane_addr + hf * 64, v[0]);
+        ptx::tmem_ld_wait(v[0]);
 #pragma unroll
-        for (int sc = 0; sc < 4; ++sc) {
-          uint32_t v[16];
-          if (MASKED) __syncwarp();                      // reconverge after the divergent skip below: tcgen05.ld is .aligned
-          ptx::tmem_ld_32x16(lane_addr + hf * 64 + sc * 16, v);
-          ptx::tmem_ld_wait();
-          const uint32_t w = MASKED ? (mw[sc >> 1] >> ((sc & 1) * 16)) & 0xFFFFu : 0u;
-          if (MASKED && w == 0xFFFFu) {                  // nothing visible in this group: P = 0
-            st_shared_v4(sP_row + (((uint32_t)(sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
-            st_shared_v4(sP_row + (((uint32_t)(sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
-            continue;
+        for (int c = 0; c < 8; ++c) {
+          const int cur = c & 1, nxt = cur ^ 1;
+          if (c < 7) {
+            if (MASKED) __syncwarp();                    // reconverge after the divergent skip below: tcgen05.ld is .aligned
+            ptx::tmem_ld_32x8(lane_addr + hf * 64 + (c + 1) * 8, v[nxt]);
           }
-          float pv[16];
+          const uint32_t w = MASKED ? (mw[c >> 2] >> ((c & 3) * 8)) & 0xFFu : 0u;
+          const uint32_t dst = sP_row + (((uint32_t)c ^ rx) << 4);
+          if (MASKED && w == 0xFFu) {                    // nothing visible in this group: P = 0
+            st_shared_v4(dst, 0u, 0u, 0u, 0u);
+          } else {
+            float pv[8];
 #pragma unroll
-          for (int k = 0; k < 16; k += 2) {
-            float s0 = __uint_as_float(v[k]), s1 = __uint_as_float(v[k + 1]);
-            if (MASKED) {
-              s0 = ((w >> k) & 1u) ? -INFINITY : s0;
-              s1 = ((w >> (k + 1)) & 1u) ? -INFINITY : s1;
+            for (int k = 0; k < 8; k += 2) {
+              float s0 = __uint_as_float(v[cur][k]), s1 = __uint_as_float(v[cur][k + 1]);
+              if (MASKED) {
+                s0 = ((w >> k) & 1u) ? -INFINITY : s0;
+                s1 = ((w >> (k + 1)) & 1u) ? -INFINITY : s1;
+              }
+              float e0, e1;
+              unpack2(fma2(pack2(s0, s1), c2p, nm2), e0, e1);
+              pv[k] = ex2(e0);
+              pv[k + 1] = ex2(e1);
+              lsum2 = add2(lsum2, pack2(pv[k], pv[k + 1]));
             }
-            float e0, e1;
-            unpack2(fma2(pack2(s0, s1), c2p, nm2), e0, e1);
-            pv[k] = ex2(e0);
-            pv[k + 1] = ex2(e1);
-            lsum2 = add2(lsum2, pack2(pv[k], pv[k + 1]));
-          }
-          if (p.thr16) {
-#pragma unroll
-            for (int q8 = 0; q8 < 2; ++q8) {             // one mixed word per 8 keys, then one multiply-add per key
-              uint32_t x = attn_mix(kbase + (uint32_t)(sc * 2 + q8) * ATTN_GOLD) * pm + pa;
+            if (p.thr16) {                               // one mixed word per 8 keys, then one multiply-add per key
+              uint32_t x = attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa;
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                pv[q8 * 8 + k] = x >= p.thr16 ? pv[q8 * 8 + k] : 0.f;
+                pv[k] = x >= p.thr16 ? pv[k] : 0.f;
                 if (k < 7) x = attn_step(x);
               }
             }
+            st_shared_v4(dst, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                         pack_bf16x2(pv[6], pv[7]));
           }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) st_row_chunk_fwd(sP_row, rx, (uint32_t)(sc * 2 + q), pv + 8 * q);
+          if (c < 7) {
+            if (MASKED) __syncwarp();
+            ptx::tmem_ld_wait(v[nxt]);
+          }
         }
       };
       if (__any_sync(0xffffffffu, (mw[0] | mw[1]) != 0u)) pass2(std::true_type{});
@@ -533,45 +552,55 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // masked tiles take a separate instantiation behind a warp-uniform branch (see the forward kernel)
         auto chunks = [&](auto masked_tag) {
           constexpr bool MASKED = decltype(masked_tag)::value;
+          // four chunks of 8 columns (= one dropout block each); the next chunk's TMEM loads are in flight while
+          // the current one is consumed
+          uint32_t sv[2][8], dv[2][8];
+          if (MASKED) __syncwarp();
+          ptx::tmem_ld_32x8(lane_addr + hf * 32, sv[0]);
+          ptx::tmem_ld_32x8(lane_addr + 64 + hf * 32, dv[0]);
+          ptx::tmem_ld_wait(sv[0], dv[0]);
+          const uint32_t kbase = rowkey + (uint32_t)((j0 + hf * 32) >> 3) * ATTN_GOLD;
 #pragma unroll
-          for (int sc = 0; sc < 2; ++sc) {             // two 16-column sub-chunks keep the register count low
-            const int cb = hf * 32 + sc * 16;
-            uint32_t sv[16], dv[16];
-            if (MASKED) __syncwarp();
-            ptx::tmem_ld_32x16(lane_addr + cb, sv);
-            ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
-            ptx::tmem_ld_wait();
-            float ds[16];
-            const uint32_t w16 = MASKED ? (w >> (sc * 16)) & 0xFFFFu : 0u;
-            const uint32_t kbase = rowkey + (uint32_t)((j0 + cb) >> 3) * ATTN_GOLD;
-            uint32_t xk = 0u;
-            if (MASKED && w16 == 0xFFFFu) {              // nothing visible in this group: dS = 0
-              st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2) ^ rx) << 4), 0u, 0u, 0u, 0u);
-              st_shared_v4(row_addr + (((uint32_t)(hf * 4 + sc * 2 + 1) ^ rx) << 4), 0u, 0u, 0u, 0u);
-              continue;
+          for (int c = 0; c < 4; ++c) {
+            const int cur = c & 1, nxt = cur ^ 1;
+            if (c < 3) {
+              if (MASKED) __syncwarp();
+              ptx::tmem_ld_32x8(lane_addr + hf * 32 + (c + 1) * 8, sv[nxt]);
+              ptx::tmem_ld_32x8(lane_addr + 64 + hf * 32 + (c + 1) * 8, dv[nxt]);
             }
+            const uint32_t w8 = MASKED ? (w >> (c * 8)) & 0xFFu : 0u;
+            const uint32_t dst = row_addr + (((uint32_t)(hf * 4 + c) ^ rx) << 4);
+            if (MASKED && w8 == 0xFFu) {                 // nothing visible in this group: dS = 0
+              st_shared_v4(dst, 0u, 0u, 0u, 0u);
+            } else {
+              float ds[8];
+              uint32_t xk = p.thr16 ? attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa : 0u;
 #pragma unroll
-            for (int k = 0; k < 16; k += 2) {
-              float e0, e1;
-              unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, nl2), e0, e1);
-              float p0 = ex2(e0), p1 = ex2(e1);
-              if (MASKED) {
-                p0 = ((w16 >> k) & 1u) ? 0.f : p0;
-                p1 = ((w16 >> (k + 1)) & 1u) ? 0.f : p1;
+              for (int k = 0; k < 8; k += 2) {
+                float e0, e1;
+                unpack2(fma2(pack2(__uint_as_float(sv[cur][k]), __uint_as_float(sv[cur][k + 1])), c2p, nl2), e0, e1);
+                float p0 = ex2(e0), p1 = ex2(e1);
+                if (MASKED) {
+                  p0 = ((w8 >> k) & 1u) ? 0.f : p0;
+                  p1 = ((w8 >> (k + 1)) & 1u) ? 0.f : p1;
+                }
+                float d0 = __uint_as_float(dv[cur][k]), d1 = __uint_as_float(dv[cur][k + 1]);
+                if (p.thr16) {
+                  d0 = xk >= p.thr16 ? d0 : 0.f;
+                  xk = attn_step(xk);
+                  d1 = xk >= p.thr16 ? d1 : 0.f;
+                  if (k != 6) xk = attn_step(xk);
+                }
+                // dS = P * (dP * keep/(1-p) - D)
+                unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
               }
-              float d0 = __uint_as_float(dv[k]), d1 = __uint_as_float(dv[k + 1]);
-              if (p.thr16) {
-                if ((k & 7) == 0) xk = attn_mix(kbase + (uint32_t)(k >> 3) * ATTN_GOLD) * pm + pa;   // new 8-key block
-                d0 = xk >= p.thr16 ? d0 : 0.f;
-                xk = attn_step(xk);
-                d1 = xk >= p.thr16 ? d1 : 0.f;
-                if ((k & 7) != 6) xk = attn_step(xk);
-              }
-              // dS = P * (dP * keep/(1-p) - D)
-              unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
+              st_shared_v4(dst, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
+                           pack_bf16x2(ds[6], ds[7]));
             }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) st_row_chunk(row_addr, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
+            if (c < 3) {
+              if (MASKED) __syncwarp();
+              ptx::tmem_ld_wait(sv[nxt], dv[nxt]);
+            }
           }
         };
         if (__any_sync(0xffffffffu, w != 0u)) chunks(std::true_type{});
@@ -741,18 +770,26 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       // masked tiles (padded keys, causal diagonal) take a separate instantiation behind a warp-uniform branch
       auto chunks = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
+        // four chunks of 8 queries (= one dropout block each); the next chunk's TMEM loads are in flight while
+        // the current one is consumed
+        uint32_t sv[2][8], dv[2][8];
+        ptx::tmem_ld_32x8(lane_addr + hf * 32, sv[0]);
+        ptx::tmem_ld_32x8(lane_addr + 64 + hf * 32, dv[0]);
+        ptx::tmem_ld_wait(sv[0], dv[0]);
+        const f32x2 c2p = pack2(c2, c2);
 #pragma unroll
-        for (int sc = 0; sc < 2; ++sc) {
-          const int cb = hf * 32 + sc * 16;
-          uint32_t sv[16], dv[16];
-          ptx::tmem_ld_32x16(lane_addr + cb, sv);
-          ptx::tmem_ld_32x16(lane_addr + 64 + cb, dv);
-          ptx::tmem_ld_wait();
-          float pd[16], ds[16];
-          const f32x2 c2p = pack2(c2, c2);
-          uint32_t xk = 0u;
+        for (int c = 0; c < 4; ++c) {
+          const int cur = c & 1, nxt = cur ^ 1;
+          const int cb = hf * 32 + c * 8;
+          if (c < 3) {
+            ptx::tmem_ld_32x8(lane_addr + cb + 8, sv[nxt]);
+            ptx::tmem_ld_32x8(lane_addr + 64 + cb + 8, dv[nxt]);
+          }
+          float pd[8], ds[8];
+          // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is 8 steps on
+          uint32_t xk = p.thr16 ? attn_mix(s_key[slot + cb] + jg) * jm + ja : 0u;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
+          for (int k4 = 0; k4 < 2; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
             const int colb = cb + k4 * 4;
             const float4 l4 = *reinterpret_cast<const float4*>(s_lse + slot + colb);
             const float4 d4 = *reinterpret_cast<const float4*>(s_dsum + slot + colb);
@@ -763,20 +800,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
               const int k = k4 * 4 + u;
               const int col = colb + u;
               float e0, e1;
-              unpack2(fma2(pack2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2p, pack2(-lv[u], -lv[u + 1])), e0, e1);
+              unpack2(fma2(pack2(__uint_as_float(sv[cur][k]), __uint_as_float(sv[cur][k + 1])), c2p, pack2(-lv[u], -lv[u + 1])), e0, e1);
               float p0 = ex2(e0), p1 = ex2(e1);
               if (MASKED) {
                 if (key_masked || col < cm) p0 = 0.f;
                 if (key_masked || col + 1 < cm) p1 = 0.f;
               }
               const f32x2 pp = pack2(p0, p1);
-              const f32x2 dd2 = pack2(__uint_as_float(dv[k]), __uint_as_float(dv[k + 1]));
+              const f32x2 dd2 = pack2(__uint_as_float(dv[cur][k]), __uint_as_float(dv[cur][k + 1]));
               if (p.thr16) {
-                // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is
-                // 8 steps on.  kf = keep/(1-p): one select per element serves both P^T*kf (dV operand) and dP*kf.
-                if ((k & 7) == 0) xk = attn_mix(s_key[slot + cb + k] + jg) * jm + ja;
+                // kf = keep/(1-p): one select per element serves both P^T*kf (dV operand) and dP*kf
                 const uint32_t x0 = xk, x1 = attn_step8(xk);
-                if ((k & 7) != 6) xk = attn_step8(x1);
+                if (k != 6) xk = attn_step8(x1);
                 const f32x2 kf = pack2(x0 >= p.thr16 ? p.inv_keep : 0.f, x1 >= p.thr16 ? p.inv_keep : 0.f);
                 unpack2(mul2(pp, kf), pd[k], pd[k + 1]);
                 // dS^T = P * (dP * keep/(1-p) - D)
@@ -788,11 +823,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
               }
             }
           }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            st_row_chunk(pd_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), pd + 8 * q);
-            st_row_chunk(ds_row, rx, (uint32_t)(hf * 4 + sc * 2 + q), ds + 8 * q);
-          }
+          st_row_chunk(pd_row, rx, (uint32_t)(hf * 4 + c), pd);
+          st_row_chunk(ds_row, rx, (uint32_t)(hf * 4 + c), ds);
+          if (c < 3) ptx::tmem_ld_wait(sv[nxt], dv[nxt]);
         }
       };
       if (__any_sync(0xffffffffu, key_masked || cm > hf * 32)) chunks(std::true_type{});

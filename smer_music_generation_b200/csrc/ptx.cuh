@@ -119,6 +119,29 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// wait for the outstanding tcgen05.ld's; the registers are operands so that no use of them can be scheduled
+// above the wait (software-pipelined loads: the next chunk is in flight while the current one is consumed)
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])::"memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])::"memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])::"memory");
+}
 
 // ---- CTA pairs (cta_group::2): two SMs of one TPC work on one 256-row tile -------------------------
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> even CTA
