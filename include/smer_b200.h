@@ -84,7 +84,9 @@ int smer_gemm_simt(const void* A, long long sam, long long sak, const void* B, l
 int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor,
                       void* C, long long ldc, int out_dtype, int M, int N, int K, const float* bias,
                       const void* resid, long long ldr, int flags, float dropout_p, uint64_t seed,
-                      uint64_t site, int split_k, void* stream);
+                      uint64_t site, int split_k, float* colsum /* nullable: [N] fp32, += column sums of C
+                      (GATE epilogue only: the bias gradient of the Linear whose input gradient C is) */,
+                      void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients) */
 int smer_colsum(const void* x, int dtype, long long ld, float* out, long long rows, int cols, void* stream);
 
@@ -94,6 +96,8 @@ typedef struct smer_attn_args {
   void* o;                    /* forward output / backward input                              */
   const void* dout;           /* backward: gradient of o                                      */
   void *dq, *dk, *dv;         /* backward outputs                                             */
+  float *dbq, *dbk, *dbv;     /* backward (tc kernels), nullable: [H*dh] fp32, += column sums of dq/dk/dv over
+                                 all tokens = the in-projection's bias gradient (transformer.py MHA in_proj_bias) */
   long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
   float* lse;                 /* [B,H,Lq] log-sum-exp of the masked scaled scores             */
   float* dsum;                /* [B,H,Lq] backward scratch: rowsum(dO*O)                      */

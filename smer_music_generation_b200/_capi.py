@@ -26,7 +26,7 @@ _vp, _ll, _i, _f, _u64 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_uint6
 
 class AttnArgs(C.Structure):
     _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("dout", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp),
-                ("ldq", _ll), ("ldk", _ll), ("ldv", _ll), ("ldo", _ll), ("lddo", _ll), ("lddq", _ll), ("lddk", _ll),
+                ("dbq", _vp), ("dbk", _vp), ("dbv", _vp), ("ldq", _ll), ("ldk", _ll), ("ldv", _ll), ("ldo", _ll), ("lddo", _ll), ("lddq", _ll), ("lddk", _ll),
                 ("lddv", _ll), ("lse", _vp), ("dsum", _vp), ("key_pad", _vp), ("kv_len", _vp), ("add_mask", _vp),
                 ("ld_mask", _ll), ("B", _i), ("H", _i), ("Lq", _i), ("Lk", _i), ("dh", _i), ("dtype", _i),
                 ("causal", _i), ("q_pos0", _i), ("scale", _f), ("dropout_p", _f), ("seed", _u64), ("site", _u64)]
@@ -60,7 +60,7 @@ _SIGS = {
     "smer_gemm_simt": (_i, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _ll, _i, _f, _u64,
                             _u64, _i, _vp]),
     "smer_gemm_bf16_tc": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _f, _u64,
-                               _u64, _i, _vp]),
+                               _u64, _i, _vp, _vp]),
     "smer_colsum": (_i, [_vp, _i, _ll, _vp, _ll, _i, _vp]),
     "smer_attn_fwd_simt": (_i, [C.POINTER(AttnArgs), _vp]),
     "smer_attn_bwd_simt": (_i, [C.POINTER(AttnArgs), _vp]),

@@ -353,6 +353,7 @@ struct BwdParams {
   bf16 *dq, *dk, *dv;
   long long lddq, lddk, lddv;
   const float* lse;
+  float *dbq, *dbk, *dbv;    // nullable: [H*DH] += column sums of dQ / dK / dV (in-projection bias gradient)
   float* dsum;               // [B,H,Lq] rowsum(dO o O): written by the dQ kernel, read by the dK/dV kernel
   const bf16 *o, *dout;      // forward output and its gradient (for dsum)
   long long ldo, lddo;
@@ -635,6 +636,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           *reinterpret_cast<uint4*>(drow + k) = u;
         }
       }
+      if (p.dbq) {                       // bias gradient of the Q projection: column sums over this CTA's 128 rows
+        float f[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) f[k] = row_ok ? __uint_as_float(v[k]) * p.scale : 0.f;
+        const float cs = warp_colsum32(f, lane);
+        atomicAdd(p.dbq + h * DH + hf * 32 + lane, cs);
+      }
     }
   }
   ptx::tc_fence_before();
@@ -861,6 +869,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           *reinterpret_cast<uint4*>(drow + k) = u;
         }
       }
+      float* db = part == 0 ? p.dbk : p.dbv;
+      if (db) {                          // bias gradient of the K / V projection
+        float f[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) f[k] = row_ok ? __uint_as_float(v[k]) * sc : 0.f;
+        const float cs = warp_colsum32(f, lane);
+        atomicAdd(db + h * DH + hf * 32 + lane, cs);
+      }
     }
   }
   ptx::tc_fence_before();
@@ -926,6 +942,7 @@ extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv;
   p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
   p.lse = a->lse; p.dsum = a->dsum; p.kv_len = a->kv_len; p.pad = a->key_pad;
+  p.dbq = a->dbq; p.dbk = a->dbk; p.dbv = a->dbv;
   p.o = (const bf16*)a->o; p.dout = (const bf16*)a->dout; p.ldo = a->ldo; p.lddo = a->lddo;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.c_log2 = a->scale * 1.4426950408889634f; p.scale = a->scale; p.causal = a->causal;

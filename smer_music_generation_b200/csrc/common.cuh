@@ -168,6 +168,22 @@ __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t site, uint64_t 
   dropout4k(dropout_key(seed, site), idx4, thr, inv_keep, m);
 }
 
+// v[c] (c = 0..31) in every lane -> the sum over the 32 lanes of column `lane` (recursive halving:
+// 31 shuffles; lane bit `off` decides which half of the remaining columns a lane keeps)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // ---------------------------------------------------------------------------------------
 // Attention-probability dropout.  Philox costs ~100 instructions per 4 elements, which would
 // make the softmax warps of the tcgen05 attention kernels the bottleneck several times over;

@@ -96,6 +96,7 @@ struct EpiParams {
   float inv_keep;
   uint64_t seed, site;
   const unsigned long long* seed_dev;
+  float* colsum;                         // nullable (GATE / generic epilogue): [N] += column sums of the stored C
   int kb_per_split, num_kb;
   int tiles_m, tiles_n, splits;          // work item w -> (split, m tile, n tile), n fastest
 };
@@ -293,9 +294,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         __syncwarp();
         const int col = n0 + chalf * (BN / 2) + hh * 32 + lc;
+        const uint32_t colmask = __ballot_sync(0xffffffffu, col < p.N);      // lanes that stay (whole (lane & 3) groups)
         if (col >= p.N) continue;                              // N % 8 == 0
         // residual / gate operands of the round's 4 row-iterations: issue all loads up front, otherwise
         // their latency serialises the epilogue past the MMA time of a K=512 tile
+        constexpr bool CAN_CSUM = EPI == EPI_GATE || EPI == EPI_GENERIC;
+        const bool f_csum = CAN_CSUM && p.colsum != nullptr;
+        float csum[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) csum[u] = 0.f;
         float rsv[4][8];
         if (has_r) {
 #pragma unroll
@@ -360,6 +367,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           store8(crow + col, v);
+          if (f_csum) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) csum[u] += v[u];
+          }
+        }
+        if (f_csum) {
+          // this round's 32 rows x 8 columns per lane group: add the 8 lanes that share (lane & 3), then one
+          // 32-byte reduction per group into the [N] fp32 vector
+#pragma unroll
+          for (int off = 4; off <= 16; off <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) csum[u] += __shfl_xor_sync(colmask, csum[u], off);
+          }
+          if ((lane >> 2) == 0) {
+            float* dst = p.colsum + col;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(csum[0]), "f"(csum[1]),
+                         "f"(csum[2]), "f"(csum[3]) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(csum[4]), "f"(csum[5]),
+                         "f"(csum[6]), "f"(csum[7]) : "memory");
+          }
         }
       }
     }
@@ -481,8 +508,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
 extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, const void* B, long long ldb, int b_kmajor,
                                  void* C, long long ldc, int out_dtype, int M, int N, int K, const float* bias,
                                  const void* resid, long long ldr, int flags, float dropout_p, uint64_t seed,
-                                 uint64_t site, int split_k, void* stream) {
+                                 uint64_t site, int split_k, float* colsum, void* stream) {
   SMER_CHECK_ARG(M > 0 && N > 0 && K > 0, "smer_gemm_bf16_tc: empty problem %dx%dx%d", M, N, K);
+  SMER_CHECK_ARG(!colsum || ((flags & SMER_EPI_GATE) && out_dtype == SMER_DT_BF16 && split_k <= 1),
+                 "smer_gemm_bf16_tc: colsum is produced by the bf16 gate epilogue only");
   SMER_CHECK_ARG(N % 8 == 0 && ldc % 8 == 0 && (!resid || ldr % 8 == 0),
                  "smer_gemm_bf16_tc: need N%%8==0 and 8-element-aligned C/resid pitches (N=%d ldc=%lld ldr=%lld)", N, ldc, ldr);
   if (split_k < 1) split_k = 1;
@@ -520,6 +549,7 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   p.thr = (dropout_p > 0.f && !(flags & SMER_EPI_GATE)) ? dropout_threshold(dropout_p) : 0u;
   p.inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   p.seed = seed; p.site = site; p.seed_dev = smer_seed_dev();
+  p.colsum = colsum;
   p.num_kb = num_kb;
   p.kb_per_split = kb_per_split;
   p.tiles_n = (N + bn - 1) / bn;

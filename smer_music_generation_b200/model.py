@@ -465,21 +465,19 @@ class _Run:
             dkv = self.new(B * Lk, 2 * d)
             q, k, v = qkv, kvbuf[:, :d], kvbuf[:, d:]
             dq, dk, dv = dqkv, dkv[:, :d], dkv[:, d:]
+        gw, gb = grads[n + "in_proj_weight"], grads[n + "in_proj_bias"]
+        # in_proj_bias gradient = column sums of dq | dk | dv, accumulated by the attention backward kernels
         a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=key_pad, kv_len=kv_len,
                           add_mask=add_mask, dropout_p=self.td, seed=self.seed, site=site_p, dout=do, dq=dq, dk=dk,
-                          dv=dv, dsum=dsum)
+                          dv=dv, dsum=dsum, dbq=gb[:d], dbk=gb[d:2 * d], dbv=gb[2 * d:])
         ops.attn_bwd(a)
-        gw, gb = grads[n + "in_proj_weight"], grads[n + "in_proj_bias"]
         dx = self.new(B * Lq, d)
         if self_attn:
-            ops.colsum(dqkv, gb)
             ops.gemm_dw(dqkv, xq, gw)
             ops.gemm_dx(dqkv, ap.w, dx, resid=resid_q)
         else:
-            ops.colsum(dqkv, gb[:d])
             ops.gemm_dw(dqkv, xq, gw[:d])
             ops.gemm_dx(dqkv, ap.w[:d], dx, resid=resid_q)
-            ops.colsum(dkv, gb[d:])
             ops.gemm_dw(dkv, xkv, gw[d:])
             ops.gemm_dx(dkv, ap.w[d:3 * d], dmem, resid=dmem)      # dmem += dkv . W_kv  (in place)
         return dx
@@ -500,8 +498,8 @@ class _Run:
         rows = df.shape[0]
         ops.gemm_dw(df, h, grads[n + "linear2.weight"])             # linear2.bias: summed inside layernorm_bwd
         dh = self.new(rows, self.ff)
-        ops.gemm_dx(df, lp.w2, dh, resid=h, flags=K.EPI_GATE, dropout_p=self.td)
-        ops.colsum(dh, grads[n + "linear1.bias"])
+        ops.gemm_dx(df, lp.w2, dh, resid=h, flags=K.EPI_GATE, dropout_p=self.td,
+                    colsum_out=grads[n + "linear1.bias"])            # linear1.bias: summed in the gate epilogue
         ops.gemm_dw(dh, x, grads[n + "linear1.weight"])
         dx = self.new(rows, self.d)
         ops.gemm_dx(dh, lp.w1, dx, resid=resid)

@@ -99,15 +99,18 @@ def gemm_nt(A, W, out, bias=None, resid=None, flags=0, dropout_p=0.0, seed=0, si
         ldr = resid.stride(0) if resid is not None else 0
         if _tc_ok(A.dtype, N, ldc, lda, ldw, ldr):
             K.check(K.lib().smer_gemm_bf16_tc(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(out), M, N, Kd, _p(bias),
-                                              _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()), "gemm_tc(nt)")
+                                              _p(resid), ldr, flags, dropout_p, seed, site, 1, 0, K.stream()), "gemm_tc(nt)")
         else:
             K.check(K.lib().smer_gemm_simt(_p(A), lda, 1, _p(W), ldw, 1, _p(out), ldc, K.dt(A), K.dt(out), M, N, Kd,
                                            _p(bias), _p(resid), ldr, flags, dropout_p, seed, site, 1, K.stream()),
                     "gemm_simt(nt)")
 
 
-def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0):
-    """out[M,Kin] = epi(dY[M,N] @ W[N,Kin]) -- input gradient of nn.Linear."""
+def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0, colsum_out=None):
+    """out[M,Kin] = epi(dY[M,N] @ W[N,Kin]) -- input gradient of nn.Linear.  `colsum_out` (fp32 [Kin], gate
+    epilogue): += column sums of `out`, i.e. the bias gradient of the Linear that produced the gated activation."""
+    fused = (colsum_out is not None and (flags & K.EPI_GATE) and out.dtype == torch.bfloat16
+             and _tc_ok(dY.dtype, W.shape[1], out.stride(0), dY.stride(0), W.stride(0), resid.stride(0) if resid is not None else 0))
     with _Timed("gemm", 2.0 * dY.shape[0] * dY.shape[1] * W.shape[1], 1):
         M, N = dY.shape
         Kin = W.shape[1]
@@ -115,10 +118,13 @@ def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0):
         ldr = resid.stride(0) if resid is not None else 0
         if _tc_ok(dY.dtype, Kin, ldc, ldy, ldw, ldr):
             K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 1, _p(W), ldw, 0, _p(out), ldc, K.dt(out), M, Kin, N, 0,
-                                              _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_tc(dx)")
+                                              _p(resid), ldr, flags, dropout_p, 0, 0, 1, _p(colsum_out) if fused else 0,
+                                              K.stream()), "gemm_tc(dx)")
         else:
             K.check(K.lib().smer_gemm_simt(_p(dY), ldy, 1, _p(W), 1, ldw, _p(out), ldc, K.dt(dY), K.dt(out), M, Kin, N,
                                            0, _p(resid), ldr, flags, dropout_p, 0, 0, 1, K.stream()), "gemm_simt(dx)")
+    if colsum_out is not None and not fused:
+        colsum(out, colsum_out)
 
 
 def gemm_dw(dY, X, out):
@@ -131,7 +137,7 @@ def gemm_dw(dY, X, out):
             tiles = ((N + 127) // 128) * ((Kin + 127) // 128)
             split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
             K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 0, _p(X), ldx, 0, _p(out), ldc, K.F32, N, Kin, M, 0, 0, 0,
-                                              K.EPI_ATOMIC, 0.0, 0, 0, split, K.stream()), "gemm_tc(dw)")
+                                              K.EPI_ATOMIC, 0.0, 0, 0, split, 0, K.stream()), "gemm_tc(dw)")
         else:
             tiles = ((N + 63) // 64) * ((Kin + 63) // 64)
             split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
@@ -146,8 +152,12 @@ def colsum(x, out):
 
 
 def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0, key_pad=None, kv_len=None,
-              add_mask=None, dropout_p=0.0, seed=0, site=0, dout=None, dq=None, dk=None, dv=None, dsum=None):
+              add_mask=None, dropout_p=0.0, seed=0, site=0, dout=None, dq=None, dk=None, dv=None, dsum=None,
+              dbq=None, dbk=None, dbv=None):
+    """dbq/dbk/dbv (fp32 [H*dh], backward): += column sums of dq/dk/dv = the in-projection's bias gradient."""
     a = K.AttnArgs()
+    a.dbq, a.dbk, a.dbv = _p(dbq), _p(dbk), _p(dbv)
+    a._db, a._dqkv = (dbq, dbk, dbv), (dq, dk, dv)      # kept for the CUDA-core path, which sums them separately
     a.q, a.k, a.v, a.o = _p(q), _p(k), _p(v), _p(o)
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
     a.dout, a.dq, a.dk, a.dv = _p(dout), _p(dq), _p(dk), _p(dv)
@@ -195,6 +205,10 @@ def attn_bwd(a):
             K.check(K.lib().smer_attn_bwd_tc(C.byref(a), K.stream()), "attn_bwd_tc")
         else:
             K.check(K.lib().smer_attn_bwd_simt(C.byref(a), K.stream()), "attn_bwd_simt")
+    if not tc:
+        for g, db in zip(a._dqkv, a._db):
+            if db is not None:
+                colsum(g, db)
 
 
 def attn_weights(a, w):

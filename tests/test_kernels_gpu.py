@@ -114,6 +114,13 @@ def test_gemm_tc_dx_dw(dev, M, N, Kin):
     act = torch.relu(torch.randn(M, Kin, generator=g)).to(dev).bfloat16()
     ops.gemm_dx(dY, W, dx, resid=act, flags=K.EPI_GATE)
     assert rel(dx, (dY.float() @ W.float()) * (act.float() > 0)) < 1e-2
+    # ... with the bias gradient (column sums of the gated result) accumulated by the same epilogue
+    cs = torch.full((Kin,), 0.25, dtype=torch.float32, device=dev)
+    dx2 = torch.empty_like(dx)
+    ops.gemm_dx(dY, W, dx2, resid=act, flags=K.EPI_GATE, colsum_out=cs)
+    assert torch.equal(dx2, dx)
+    want = ((dY.float() @ W.float()) * (act.float() > 0)).sum(0) + 0.25
+    assert (cs - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
     dw = torch.zeros(N, Kin, dtype=torch.float32, device=dev)
     ops.gemm_dw(dY, X, dw)
     assert rel(dw, dY.float().t() @ X.float()) < 2e-5
@@ -362,11 +369,17 @@ def test_attention_tc_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
         dqkv = torch.full((B * Lq, 3 * d), float("nan"), dtype=torch.bfloat16, device=dev)
         dkv = torch.full((B * Lk, 2 * d), float("nan"), dtype=torch.bfloat16, device=dev)
         dsum = torch.empty(B, H, Lq, device=dev)
+        db = torch.full((3 * d,), 0.5, dtype=torch.float32, device=dev)      # bias-gradient accumulators (+=)
         a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=pad, kv_len=kv_len,
-                          dropout_p=drop, seed=77, site=3, dout=do, dq=dqkv[:, :d], dk=dkv[:, :d], dv=dkv[:, d:], dsum=dsum)
+                          dropout_p=drop, seed=77, site=3, dout=do, dq=dqkv[:, :d], dk=dkv[:, :d], dv=dkv[:, d:], dsum=dsum,
+                          dbq=db[:d], dbk=db[d:2 * d], dbv=db[2 * d:])
         ops.attn_bwd(a)
         torch.cuda.synchronize()
         grads[path] = (dqkv[:, :d].clone(), dkv[:, :d].clone(), dkv[:, d:].clone())
+        # in-projection bias gradient = column sums of dq | dk | dv (fused into the tcgen05 kernels' epilogues)
+        want = torch.cat([x.float().sum(0) for x in grads[path]]) + 0.5
+        tol = 2e-2 * max(1.0, want.abs().max().item())
+        assert (db - want).abs().max().item() < tol, (path, (db - want).abs().max().item(), tol)
     ops._TC_ATTN = "tc"
     for name, x, y in zip(("dq", "dk", "dv"), grads["tc"], grads["simt"]):
         assert torch.isfinite(x.float()).all(), name
