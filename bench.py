@@ -414,7 +414,10 @@ def run_decode(args):
     res = None
     times, dev_times = [], []
     gens = []
+    clocks = None
     for it in range(args.warmup + args.steps):
+        if it == args.warmup and rank == 0:
+            clocks = ClockSampler(local)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -427,6 +430,7 @@ def run_decode(args):
             times.append(e0.elapsed_time(e1))           # whole call: host packing, H2D, encoder, decode, D2H, unpacking
             dev_times.append(res["device_ms"])          # encoder + cross K/V + graph capture + decode loop
             gens.append(sum(res["generated"]))
+    clk = clocks.stop() if clocks else None
     ms = sum(times)
     ms_dev = sum(dev_times)
     toks = float(sum(gens))
@@ -460,7 +464,7 @@ def run_decode(args):
                                     "e2e: whole InfillDecoder.generate() incl. host packing, H2D, D2H of the token streams"},
                 "e2e": {"value": toks / (ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": dec.h2d_bytes,
                         "d2h_bytes_per_step": dec.d2h_bytes, "ms_per_step": ms / args.steps},
-                "gpu_launches": kl, "decode_steps": res["steps"], "roofline": roof,
+                "clocks": clk, "gpu_launches": kl, "decode_steps": res["steps"], "roofline": roof,
                 "step_ms_graph": ms_dev / args.steps / max(1, res["steps"]),
                 "hbm_bytes_per_step_algorithmic": pr["cross"]["bytes"] + pr["self"]["bytes"]}
         print(json.dumps(line), flush=True)

@@ -45,12 +45,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
       "@P bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)     // suspend-time hint: the waiting thread sleeps in hardware instead of spinning
-      : "memory");
+      "r"(parity)      // (no suspend-time hint: ptxas turns it into NANOSLEEP back-off, which made the latency of the
+      : "memory");     //  small decode GEMMs jitter by 2x; the plain form re-polls at the hardware's own short limit)
 }
 
 // ---- TMA --------------------------------------------------------------------------------

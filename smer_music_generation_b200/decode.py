@@ -388,19 +388,23 @@ class InfillDecoder:
                 t.copy_(c)
             for kv in self.self_kv:
                 pass                                   # row 0 is rewritten by the first real step
+            # one graph = `check_every` decode steps (the steps between two done-checks): one launch per check
+            # interval keeps the device fed even when the host is slow
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._step(0)
+                for _ in range(check_every):
+                    self._step(0)
             for t, c in zip((self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx, self.done,
                              self.gen_count, self.state), snap):
                 t.copy_(c)
         while steps < max_steps:
-            for _ in range(check_every):
-                if self.graph is not None:
-                    self.graph.replay()
-                else:
+            if self.graph is not None:
+                self.graph.replay()
+                steps += check_every
+            else:
+                for _ in range(check_every):
                     self._step(steps)
-                steps += 1
+                    steps += 1
             if bool(self.done.all().item()):           # one small D2H every `check_every` tokens
                 break
         self.steps_run = steps
