@@ -530,13 +530,13 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   // 128x256 tiles when they still fill the GPU (and N is wide enough to use them); CTA pairs
   // (256x256 tiles, cta_group::2) when there are enough of those for every pair of SMs
   static const bool allow_2sm = [] { const char* e = getenv("SMER_GEMM_2SM"); return !(e && e[0] == '0'); }();
-  const bool wide = N >= 256 && (long long)tiles_m * ((N + 255) / 256) * split_k >= sms;
+  const bool wide = N >= 256 && (long long)tiles_m * ((N + 255) / 256) * split_k * 20 >= sms * 19;      // >= 95 % of the SMs
   // (measured on B200: a CTA of a pair stages half of B, one third less smem fill + operand traffic per MMA:
   //  1243 vs 1083 TFLOP/s at K=2048, 987 vs 915-932 at K=512 with N >= 1536; the N=512, K=512 out-projection
   //  has too few items per pair and stays on single CTAs: 700 vs 648)
   static const bool force_2sm = [] { const char* e = getenv("SMER_GEMM_2SM"); return e && e[0] == '2'; }();
   const bool pair = allow_2sm && wide && (kb_per_split >= 16 || N >= 1024 || force_2sm) &&
-                    (long long)((M + 255) / 256) * ((N + 255) / 256) * split_k >= sms / 2;
+                    (long long)((M + 255) / 256) * ((N + 255) / 256) * split_k * 20 >= (sms / 2) * 19;
   const int bn = wide ? 256 : 128;
   if (a_kmajor) rc = smer_make_tmap_bf16(&ta, A, K, M, lda, BK, BM);
   else rc = smer_make_tmap_bf16(&ta, A, M, K, lda, 64, BK);

@@ -397,7 +397,11 @@ class InfillDecoder:
             for t, c in zip((self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx, self.done,
                              self.gen_count, self.state), snap):
                 t.copy_(c)
+        trace = [] if getattr(self, "trace_intervals", False) else None     # diagnostics: device time per check interval
         while steps < max_steps:
+            if trace is not None:
+                trace.append(torch.cuda.Event(enable_timing=True))
+                trace[-1].record()
             if self.graph is not None:
                 self.graph.replay()
                 steps += check_every
@@ -413,6 +417,9 @@ class InfillDecoder:
         ev1.record()
         ev1.synchronize()
         self.device_ms = self._ev0.elapsed_time(ev1)              # encoder + cross K/V + decode loop on the device
+        if trace is not None:
+            trace.append(ev1)
+            self.interval_ms = [a.elapsed_time(b) for a, b in zip(trace[:-1], trace[1:])]
         tok = self.tok_buf.cpu()
         lens = self.cur_len.cpu()
         gen = self.gen_count.cpu()

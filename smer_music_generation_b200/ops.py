@@ -127,6 +127,29 @@ def gemm_dx(dY, W, out, resid=None, flags=0, dropout_p=0.0, colsum_out=None):
         colsum(out, colsum_out)
 
 
+def _dw_split(N, Kin, M):
+    """K-split of the weight-gradient GEMM (K = M tokens).  With 256x256 CTA-pair tiles: the split count whose
+    item count fills whole rounds of SM pairs (>= 16 k-blocks per item, fewest splits among the best)."""
+    kb = (M + 63) // 64
+    pairs = max(1, num_sms() // 2)
+    if N >= 256 and Kin >= 256:
+        t = ((N + 255) // 256) * ((Kin + 255) // 256)
+        best = None
+        for s in range(1, max(1, kb // 16) + 1):
+            items = t * s
+            if items * 20 < pairs * 19:
+                continue
+            eff = items / (-(-items // pairs) * pairs)
+            if best is None or eff > best[0]:
+                best = (eff, s)
+            if eff >= 0.95 or s * t > 6 * pairs:
+                break
+        if best is not None:
+            return best[1]
+    tiles = ((N + 127) // 128) * ((Kin + 127) // 128)
+    return max(1, min(kb, (2 * num_sms()) // tiles))
+
+
 def gemm_dw(dY, X, out):
     """out[N,Kin] += dY[M,N]^T @ X[M,Kin] (fp32, `out` pre-zeroed) -- weight gradient of nn.Linear."""
     with _Timed("gemm_dw", 2.0 * dY.shape[0] * dY.shape[1] * X.shape[1], 1):
@@ -134,8 +157,7 @@ def gemm_dw(dY, X, out):
         Kin = X.shape[1]
         ldy, ldx, ldc = dY.stride(0), X.stride(0), out.stride(0)
         if _tc_ok(dY.dtype, Kin, ldc, ldy, ldx):
-            tiles = ((N + 127) // 128) * ((Kin + 127) // 128)
-            split = max(1, min((M + 63) // 64, (2 * num_sms()) // tiles))
+            split = _dw_split(N, Kin, M)
             K.check(K.lib().smer_gemm_bf16_tc(_p(dY), ldy, 0, _p(X), ldx, 0, _p(out), ldc, K.F32, N, Kin, M, 0, 0, 0,
                                               K.EPI_ATOMIC, 0.0, 0, 0, split, 0, K.stream()), "gemm_tc(dw)")
         else:
