@@ -97,7 +97,8 @@ def lib():
                     raise RuntimeError(
                         f"{LIB_PATH} not found: build it with `python -m smer_music_generation_b200.build` "
                         "(the SMER B200 path has no CPU fallback)")
-                l = C.CDLL(LIB_PATH)
+                # SMER_B200_LIB: another build of the same library (A/B timing of kernel variants on one box)
+                l = C.CDLL(os.environ.get("SMER_B200_LIB") or LIB_PATH)
                 for name, (res, args) in _SIGS.items():
                     fn = getattr(l, name)
                     fn.restype = res

@@ -30,7 +30,8 @@ constexpr int BM = 128, BN = 128, DH = 64;
 constexpr int TILE_QKV = BM * DH * 2;            // 16 KB
 constexpr int TILE_P = BM * BN * 2;              // 32 KB (two 64-key halves of 16 KB)
 constexpr int FWD_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
-constexpr int FWD_SMEM = 3 * TILE_QKV + TILE_P + 1024 /*align*/ + 2560 /*barriers + row exchange*/;
+constexpr int MASK_WORDS = 512;                    // key-mask bitmap of one batch row: Lk <= 16384
+constexpr int FWD_SMEM = 3 * TILE_QKV + TILE_P + 1024 /*align*/ + 2560 /*barriers + row exchange*/ + MASK_WORDS * 4;
 constexpr int TMEM_COLS = 256;
 constexpr int O_COL = 128;
 
@@ -78,8 +79,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *k_empty = bars + 3, *v_empty = bars + 4,
            *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  uint32_t* padw = tmem_ptr + 2;                 // [2][4] mask words of the current KV tile
   float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 parity][2 halves][128 rows]
+  uint32_t* mask_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 2560);   // bit j: key j masked
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;     // heavy (late-causal) query tiles first
@@ -166,20 +167,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    // key-mask bitmap of all the tiles this CTA visits, built once (one barrier instead of one per tile)
+    const bool use_mask = p.pad != nullptr || (kend & (BN - 1)) != 0;
+    if (use_mask) {
+      for (int j = (warp - 2) * 32 + lane; j < ntiles * BN; j += 256) {
+        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
+        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
+        if (lane == 0) mask_all[j >> 5] = bal;
+      }
+      bar_sync_bwd();
+    }
 
     for (int t = 0; t < ntiles; ++t) {
       const int j0 = t * BN;
       uint32_t mw[2] = {0u, 0u};
-      if (p.pad != nullptr || j0 + BN > kend) {
-        if (hf == 0) {
-          const int j = j0 + r;
-          const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
-          const uint32_t bal = __ballot_sync(0xffffffffu, msk);
-          if (lane == 0) padw[(t & 1) * 4 + quarter] = bal;
-        }
-        bar_sync_bwd();
-        mw[0] = padw[(t & 1) * 4 + hf * 2];
-        mw[1] = padw[(t & 1) * 4 + hf * 2 + 1];
+      if (use_mask) {
+        mw[0] = mask_all[(j0 >> 5) + hf * 2];
+        mw[1] = mask_all[(j0 >> 5) + hf * 2 + 1];
       }
       if (p.causal && j0 + BN - 1 > i0) {
 #pragma unroll
@@ -346,7 +350,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int BKV = 64;                         // second tile dimension of both backward kernels
 constexpr int TILE_HALF = BKV * DH * 2;         // 8 KB
 constexpr int BWD_THREADS = 320;          // TMA warp, MMA warp, 8 softmax warps (2 threads per TMEM lane)
-constexpr int DQ_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + TILE_QKV + 1024 + 1536;    // + barriers, mask words, dsum exchange
+constexpr int DQ_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + TILE_QKV + 1024 + 1536 + MASK_WORDS * 4;    // + barriers, dsum exchange, key-mask bitmap
 constexpr int DKV_SMEM = 2 * TILE_QKV + 4 * TILE_HALF + 2 * TILE_QKV + 1024 + 2048;
 
 struct BwdParams {
@@ -418,7 +422,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_empty = bars + 3 /*[2]*/, *sp_full = bars + 5,
            *ds_full = bars + 6, *dq_done = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  uint32_t* padw = tmem_ptr + 2;                     // [2][2]
+  uint32_t* mask_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 1536);   // bit j: key j masked
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;
@@ -518,6 +522,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       unpack2(acc2, d0, d1);
       dsum = d0 + d1;
     }
+    // key-mask bitmap of all the tiles this CTA visits, built once (published by the barrier below)
+    const bool use_mask = p.pad != nullptr || (kend & (BKV - 1)) != 0;
+    if (use_mask) {
+      for (int j = (warp - 2) * 32 + lane; j < ntiles * BKV; j += 256) {
+        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
+        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
+        if (lane == 0) mask_all[j >> 5] = bal;
+      }
+    }
     {
       float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][128]
       xch[hf * 128 + r] = dsum;
@@ -529,14 +542,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int t = 0; t < ntiles; ++t) {
       const int j0 = t * BKV;
       uint32_t mw[2] = {0u, 0u};
-      if (p.pad != nullptr || j0 + BKV > kend) {
-        const int j = j0 + (r & 63);
-        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
-        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
-        if (lane == 0) padw[(t & 1) * 2 + (quarter & 1)] = bal;       // quarters 0/2 and 1/3 write equal words
-        bar_sync_bwd();
-        mw[0] = padw[(t & 1) * 2];
-        mw[1] = padw[(t & 1) * 2 + 1];
+      if (use_mask) {
+        mw[0] = mask_all[j0 >> 5];
+        mw[1] = mask_all[(j0 >> 5) + 1];
       }
       if (p.causal && j0 + BKV - 1 > i0) {
 #pragma unroll
@@ -895,6 +903,7 @@ int check_common(const smer_attn_args* a, const char* who) {
     return SMER_ERR_UNSUPPORTED;
   }
   if (a->causal && a->Lq != a->Lk) { smer_set_error("%s: causal needs Lq == Lk", who); return SMER_ERR_UNSUPPORTED; }
+  if (a->Lk > MASK_WORDS * 32) { smer_set_error("%s: Lk <= %d (key-mask bitmap in shared memory)", who, MASK_WORDS * 32); return SMER_ERR_UNSUPPORTED; }
   if (a->B <= 0 || a->H <= 0 || a->Lq <= 0 || a->Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }
   return SMER_OK;
 }

@@ -201,7 +201,7 @@ def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0,
 
 def _attn_tc_ok(a) -> bool:
     return (_TC_ATTN == "tc" and a.dtype == K.BF16 and a.dh == 64 and not a.add_mask and a.q_pos0 == 0
-            and (not a.causal or a.Lq == a.Lk)
+            and (not a.causal or a.Lq == a.Lk) and a.Lk <= 16384
             and all(x % 8 == 0 for x in (a.ldq, a.ldk, a.ldv, a.ldo))
             and all((x or 0) % 16 == 0 for x in (a.q, a.k, a.v, a.o)))
 
