@@ -340,12 +340,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // =========================================================================================
 // BACKWARD.  Two kernels, both with the forward's warp roles (TMA producer / MMA issuer /
 // 128 softmax threads, thread <-> TMEM lane) and two CTAs per SM:
-//   dQ kernel  : CTA = 128 query rows, loop over 64-key tiles.  S = Q K^T and dP = dO V^T into
-//                TMEM; threads form dS = P o (dP*keep/(1-p) - D) in bf16 (smem, A operand);
+//   dQ kernel  : CTA = 128 query rows, 64-key K/V tiles processed as two 32-key sub-tiles with their own
+//                S = Q K^T / dP = dO V^T buffers in TMEM, so the MMAs of the next sub-tile run while the
+//                threads form dS = P o (dP*keep/(1-p) - D) in bf16 (smem, A operand) of the current one;
 //                dQ += dS K accumulates in TMEM over the whole loop (no rescale in backward).
+//                (The same two-buffer split of the dK/dV kernel measured 8 % slower and was dropped.)
 //   dKV kernel : CTA = 128 keys, loop over 64-query tiles.  S^T = K Q^T, dP^T = V dO^T; threads
 //                (<-> key row) write P^T*keep and dS^T; dV += P^T dO, dK += dS^T Q in TMEM.
-// P is recomputed from the saved log-sum-exp; D = rowsum(dO o O) comes from a small pre-kernel.
+// P is recomputed from the saved log-sum-exp; D = rowsum(dO o O) is formed by the dQ kernel's prologue.
 // =========================================================================================
 constexpr int BKV = 64;                         // second tile dimension of both backward kernels
 constexpr int TILE_HALF = BKV * DH * 2;         // 8 KB
@@ -410,257 +412,6 @@ __global__ void attn_dsum_kernel(const T* __restrict__ o, long long ldo, const T
 
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sdO = smem + TILE_QKV;
-  uint8_t* sK = smem + 2 * TILE_QKV;                 // [2] x 8 KB
-  uint8_t* sV = sK + 2 * TILE_HALF;                  // [2] x 8 KB
-  uint8_t* sdS = sV + 2 * TILE_HALF;                 // 16 KB: [128 q][64 keys] K-major
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_QKV);
-  uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_empty = bars + 3 /*[2]*/, *sp_full = bars + 5,
-           *ds_full = bars + 6, *dq_done = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  uint32_t* mask_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 1536);   // bit j: key j masked
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int i0 = qt * BM;
-  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
-  if (p.causal) kend = min(kend, i0 + BM);
-  const int ntiles = (kend + BKV - 1) / BKV;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 256 : 1);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (ptx::elect_one() && ntiles > 0) {
-      ptx::mbar_expect_tx(qdo_full, 2 * TILE_QKV);
-      ptx::tma_load_2d(sQ, &tmQ, qdo_full, h * DH, b * p.Lq + i0);
-      ptx::tma_load_2d(sdO, &tmdO, qdo_full, h * DH, b * p.Lq + i0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        if (t >= 2) ptx::mbar_wait(kv_empty + s, ((t - 2) >> 1) & 1);
-        ptx::mbar_expect_tx(kv_full + s, 2 * TILE_HALF);
-        ptx::tma_load_2d(sK + s * TILE_HALF, &tmK, kv_full + s, h * DH, b * p.Lk + t * BKV);
-        ptx::tma_load_2d(sV + s * TILE_HALF, &tmV, kv_full + s, h * DH, b * p.Lk + t * BKV);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (ptx::elect_one() && ntiles > 0) {
-      constexpr uint32_t idesc_kk = ptx::make_idesc_bf16(BM, BKV, 0, 0);     // both operands K-major
-      constexpr uint32_t idesc_kn = ptx::make_idesc_bf16(BM, DH, 0, 1);      // B MN-major
-      const uint32_t aQ = ptx::smem_u32(sQ), adO = ptx::smem_u32(sdO), adS = ptx::smem_u32(sdS);
-      ptx::mbar_wait(qdo_full, 0);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const uint32_t aK = ptx::smem_u32(sK + s * TILE_HALF), aV = ptx::smem_u32(sV + s * TILE_HALF);
-        ptx::mbar_wait(kv_full + s, (t >> 1) & 1);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          ptx::umma_bf16_ss(tmem_base, ptx::make_smem_desc(aQ + k * 32, 16, 1024), ptx::make_smem_desc(aK + k * 32, 16, 1024),
-                            idesc_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          ptx::umma_bf16_ss(tmem_base + 64, ptx::make_smem_desc(adO + k * 32, 16, 1024),
-                            ptx::make_smem_desc(aV + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
-        ptx::umma_commit(sp_full);
-        ptx::mbar_wait(ds_full, t & 1);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          ptx::umma_bf16_ss(tmem_base + 128, ptx::make_smem_desc(adS + k * 32, 16, 1024),
-                            ptx::make_smem_desc(aK + k * 2048, 8192, 1024), idesc_kn, (t > 0 || k > 0) ? 1u : 0u);
-        ptx::umma_commit(kv_empty + s);
-      }
-      ptx::umma_commit(dq_done);
-    }
-    __syncwarp();
-  } else {
-    const int quarter = warp & 3;
-    const int hf = (warp - 2) >> 2;                    // this thread's 32 of the tile's 64 key columns / dQ columns
-    const int r = quarter * 32 + lane;
-    const int i = i0 + r;
-    const bool row_ok = i < p.Lq;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t row_addr = ptx::smem_u32(sdS) + r * 128;
-    const uint32_t rx = (uint32_t)(r & 7);
-    const int ii = row_ok ? i : p.Lq - 1;
-    const long long rowid = ((long long)b * p.H + h) * p.Lq + ii;
-    const uint32_t rowkey = p.thr16 ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 7)) : 0u;
-    uint32_t pm = 1u, pa = 0u;                     // row (ii & 7) of the 8x8 dropout block: 8 steps per row
-    if (p.thr16) attn_advance(8 * (ii & 7), pm, pa);
-    float lse2 = INFINITY, dsum = 0.f;
-    if (row_ok) {
-      const float l = p.lse[rowid];
-      lse2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
-      // D_i = sum_c dO[i,c] * O[i,c]: this thread's 32 of the 64 columns (64 B of each row), then the pair's sum
-      const uint4* orow = reinterpret_cast<const uint4*>(p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH + hf * 32);
-      const uint4* grow = reinterpret_cast<const uint4*>(p.dout + ((long long)b * p.Lq + i) * p.lddo + h * DH + hf * 32);
-      f32x2 acc2 = pack2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 ov = orow[c], gv = grow[c];
-        acc2 = fma2(bf2_to_f2(ov.x), bf2_to_f2(gv.x), acc2);
-        acc2 = fma2(bf2_to_f2(ov.y), bf2_to_f2(gv.y), acc2);
-        acc2 = fma2(bf2_to_f2(ov.z), bf2_to_f2(gv.z), acc2);
-        acc2 = fma2(bf2_to_f2(ov.w), bf2_to_f2(gv.w), acc2);
-      }
-      float d0, d1;
-      unpack2(acc2, d0, d1);
-      dsum = d0 + d1;
-    }
-    // key-mask bitmap of all the tiles this CTA visits, built once (published by the barrier below)
-    const bool use_mask = p.pad != nullptr || (kend & (BKV - 1)) != 0;
-    if (use_mask) {
-      for (int j = (warp - 2) * 32 + lane; j < ntiles * BKV; j += 256) {
-        const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
-        const uint32_t bal = __ballot_sync(0xffffffffu, msk);
-        if (lane == 0) mask_all[j >> 5] = bal;
-      }
-    }
-    {
-      float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][128]
-      xch[hf * 128 + r] = dsum;
-      bar_sync_bwd();
-      dsum += xch[(hf ^ 1) * 128 + r];
-      if (row_ok && hf == 0) p.dsum[rowid] = dsum;             // for the dK/dV kernel that follows on the stream
-    }
-    const float c2 = p.c_log2;
-    for (int t = 0; t < ntiles; ++t) {
-      const int j0 = t * BKV;
-      uint32_t mw[2] = {0u, 0u};
-      if (use_mask) {
-        mw[0] = mask_all[j0 >> 5];
-        mw[1] = mask_all[(j0 >> 5) + 1];
-      }
-      if (p.causal && j0 + BKV - 1 > i0) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int nvis = i - (j0 + c * 32) + 1;
-          mw[c] |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
-        }
-      }
-      ptx::mbar_wait(sp_full, t & 1);
-      ptx::tc_fence_after();
-      {
-        const uint32_t w = mw[hf];
-        const f32x2 c2p = pack2(c2, c2), nl2 = pack2(-lse2, -lse2), ik2 = pack2(p.inv_keep, p.inv_keep), nd2 = pack2(-dsum, -dsum);
-        // masked tiles take a separate instantiation behind a warp-uniform branch (see the forward kernel)
-        auto chunks = [&](auto masked_tag) {
-          constexpr bool MASKED = decltype(masked_tag)::value;
-          // four chunks of 8 columns (= one dropout block each); the next chunk's TMEM loads are in flight while
-          // the current one is consumed
-          uint32_t sv[2][8], dv[2][8];
-          if (MASKED) __syncwarp();
-          ptx::tmem_ld_32x8(lane_addr + hf * 32, sv[0]);
-          ptx::tmem_ld_32x8(lane_addr + 64 + hf * 32, dv[0]);
-          ptx::tmem_ld_wait(sv[0], dv[0]);
-          const uint32_t kbase = rowkey + (uint32_t)((j0 + hf * 32) >> 3) * ATTN_GOLD;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int cur = c & 1, nxt = cur ^ 1;
-            if (c < 3) {
-              if (MASKED) __syncwarp();
-              ptx::tmem_ld_32x8(lane_addr + hf * 32 + (c + 1) * 8, sv[nxt]);
-              ptx::tmem_ld_32x8(lane_addr + 64 + hf * 32 + (c + 1) * 8, dv[nxt]);
-            }
-            const uint32_t w8 = MASKED ? (w >> (c * 8)) & 0xFFu : 0u;
-            const uint32_t dst = row_addr + (((uint32_t)(hf * 4 + c) ^ rx) << 4);
-            if (MASKED && w8 == 0xFFu) {                 // nothing visible in this group: dS = 0
-              st_shared_v4(dst, 0u, 0u, 0u, 0u);
-            } else {
-              float ds[8];
-              uint32_t xk = p.thr16 ? attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa : 0u;
-#pragma unroll
-              for (int k = 0; k < 8; k += 2) {
-                float e0, e1;
-                unpack2(fma2(pack2(__uint_as_float(sv[cur][k]), __uint_as_float(sv[cur][k + 1])), c2p, nl2), e0, e1);
-                float p0 = ex2(e0), p1 = ex2(e1);
-                if (MASKED) {
-                  p0 = ((w8 >> k) & 1u) ? 0.f : p0;
-                  p1 = ((w8 >> (k + 1)) & 1u) ? 0.f : p1;
-                }
-                float d0 = __uint_as_float(dv[cur][k]), d1 = __uint_as_float(dv[cur][k + 1]);
-                if (p.thr16) {
-                  d0 = xk >= p.thr16 ? d0 : 0.f;
-                  xk = attn_step(xk);
-                  d1 = xk >= p.thr16 ? d1 : 0.f;
-                  if (k != 6) xk = attn_step(xk);
-                }
-                // dS = P * (dP * keep/(1-p) - D)
-                unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
-              }
-              st_shared_v4(dst, pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]), pack_bf16x2(ds[4], ds[5]),
-                           pack_bf16x2(ds[6], ds[7]));
-            }
-            if (c < 3) {
-              if (MASKED) __syncwarp();
-              ptx::tmem_ld_wait(sv[nxt], dv[nxt]);
-            }
-          }
-        };
-        if (__any_sync(0xffffffffu, w != 0u)) chunks(std::true_type{});
-        else chunks(std::false_type{});
-      }
-      ptx::fence_proxy_async();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(ds_full);
-    }
-    if (ntiles > 0) {
-      ptx::mbar_wait(dq_done, 0);
-      ptx::tc_fence_after();
-    }
-    bf16* drow = p.dq + ((long long)b * p.Lq + i) * p.lddq + h * DH + hf * 32;
-    {
-      uint32_t v[32];
-      if (ntiles > 0) {                    // warp-uniform: tcgen05.ld is .sync.aligned
-        ptx::tmem_ld_32x32(lane_addr + 128 + hf * 32, v);
-        ptx::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = 0u;
-      }
-      if (row_ok) {
-#pragma unroll
-        for (int k = 0; k < 32; k += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[k]) * p.scale, __uint_as_float(v[k + 1]) * p.scale);
-          u.y = pack_bf16x2(__uint_as_float(v[k + 2]) * p.scale, __uint_as_float(v[k + 3]) * p.scale);
-          u.z = pack_bf16x2(__uint_as_float(v[k + 4]) * p.scale, __uint_as_float(v[k + 5]) * p.scale);
-          u.w = pack_bf16x2(__uint_as_float(v[k + 6]) * p.scale, __uint_as_float(v[k + 7]) * p.scale);
-          *reinterpret_cast<uint4*>(drow + k) = u;
-        }
-      }
-      if (p.dbq) {                       // bias gradient of the Q projection: column sums over this CTA's 128 rows
-        float f[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) f[k] = row_ok ? __uint_as_float(v[k]) * p.scale : 0.f;
-        const float cs = warp_colsum32(f, lane);
-        atomicAdd(p.dbq + h * DH + hf * 32 + lane, cs);
-      }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-
-__global__ void __launch_bounds__(BWD_THREADS, 2)
-attn_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1216,7 +967,6 @@ extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   static bool attr_set = false;
   if (!attr_set) {
     SMER_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
-    SMER_CUDA(cudaFuncSetAttribute(attn_bwd_dq_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     SMER_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     attr_set = true;
   }
@@ -1227,10 +977,7 @@ extern "C" int smer_attn_bwd_tc(const smer_attn_args* a, void* stream) {
   if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, rk, a->ldk, DH, BKV))) return rc;
   if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, rk, a->ldv, DH, BKV))) return rc;
   dim3 gq((a->Lq + BM - 1) / BM, a->H, a->B);
-  // two-buffer sub-tile pipeline by default; SMER_ATTN_BWD_PIPE=0 selects the one-buffer kernels (A/B timing)
-  static const bool pipe = [] { const char* e = getenv("SMER_ATTN_BWD_PIPE"); return !(e && e[0] == '0'); }();
-  if (pipe) attn_bwd_dq_pipe_kernel<<<gq, BWD_THREADS, DQ_SMEM, st>>>(tq, tdo, tk, tv, p);
-  else attn_bwd_dq_tc_kernel<<<gq, BWD_THREADS, DQ_SMEM, st>>>(tq, tdo, tk, tv, p);
+  attn_bwd_dq_tc_kernel<<<gq, BWD_THREADS, DQ_SMEM, st>>>(tq, tdo, tk, tv, p);
   // dKV kernel: 64-row Q / dO boxes, 128-row K / V boxes
   if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, rq, a->ldq, DH, BKV))) return rc;
   if ((rc = smer_make_tmap_bf16(&tdo, a->dout, dcols, rq, a->lddo, DH, BKV))) return rc;
