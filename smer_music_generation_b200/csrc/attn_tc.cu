@@ -380,35 +380,6 @@ __device__ __forceinline__ void st_row_chunk(uint32_t row_addr, uint32_t rx, uin
                pack_bf16x2(v[6], v[7]));
 }
 
-template <typename T>
-__global__ void attn_dsum_kernel(const T* __restrict__ o, long long ldo, const T* __restrict__ g, long long ldg,
-                                 float* __restrict__ dsum, int B, int H, int Lq) {
-  // 8 lanes per (row, head): 16-byte loads, shuffle reduction
-  long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 3;
-  int part = threadIdx.x & 7;
-  long long n = (long long)B * Lq * H;
-  if (t >= n) return;
-  int h = (int)(t % H);
-  long long row = t / H;                         // b*Lq + i
-  uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + h * DH + part * 8);
-  uint4 c = *reinterpret_cast<const uint4*>(g + row * ldg + h * DH + part * 8);
-  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c);
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float2 x = __bfloat1622float2(pa[k]), y = __bfloat1622float2(pc[k]);
-    s = fmaf(x.x, y.x, s);
-    s = fmaf(x.y, y.y, s);
-  }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (part == 0) {
-    int b = (int)(row / Lq), i = (int)(row % Lq);
-    dsum[((long long)b * H + h) * Lq + i] = s;
-  }
-}
 
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
