@@ -129,6 +129,15 @@ int smer_xent_bwd(const float* logits, long long ld, const int64_t* targets, con
                   int Vpad, float grad_scale, const float* grad_scale_dev /* device scalar or NULL */,
                   void* stream);
 
+/* Token accuracy by target class -- the metric loop of train.py:988-1034 (`accuracy()`: argmax of every row,
+ * pad targets skipped, one counter pair per vocab.token_class_ranges class plus the total).
+ * class_of[V]: class index of a token id or -1; counts (DEVICE, caller-zeroed, +=): [0..ncls) correct per
+ * class, [ncls] correct total, [ncls+1 .. 2*ncls+1) tokens per class, [2*ncls+1] tokens total.
+ * argmax_out (nullable): [rows] first-maximum index of every row (torch.argmax). */
+#define SMER_ACC_MAX_CLASSES 30
+int smer_token_accuracy(const float* logits, long long ld, const int64_t* targets, const int* class_of, int ncls,
+                        unsigned long long* counts, int64_t* argmax_out, long long rows, int V, void* stream);
+
 /* ---- K11: Adam.  train.py:264,786 ------------------------------------------------------------ */
 int smer_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
                    float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);

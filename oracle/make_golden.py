@@ -219,6 +219,69 @@ def golden_decode(vocab, name="decode_greedy.pt", all_controls=tuple(range(242, 
     print("decode steps:", len(steps), "S =", len(src))
 
 
+def reference_function(path, name, namespace):
+    """Compiles ONE function of a reference script without importing the script (train.py cannot be
+    imported here: coloredlogs / wandb.login at import time, train.py:8,25) and returns it."""
+    import ast
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    code = compile(ast.Module(body=[fn], type_ignores=[]), path, "exec")
+    exec(code, namespace)
+    return namespace[name]
+
+
+def golden_metrics(vocab):
+    """train.py:988-1034 `accuracy()` run on the golden forward's logits: per-class and total token
+    accuracy, plus the class table it looks targets up in (vocab.py:159-300)."""
+    accuracy = reference_function(os.path.join(REF, "train.py"), "accuracy", {"torch": torch})
+    fw = torch.load(os.path.join(OUT, "fwd_small.pt"))
+    logits, tgt_out = fw["logits"], fw["tgt_out"]
+    # make the argmax interesting: push half of the positions to their target, keep a few exact ties
+    g = torch.Generator().manual_seed(5)
+    lg = logits.clone()
+    hit = torch.rand(tgt_out.shape, generator=g) < 0.5
+    lg.scatter_add_(2, tgt_out[..., None], (hit.float() * 8.0)[..., None])
+    lg[0, 3, 200] = lg[0, 3].max() + 1.0
+    lg[0, 3, 150] = lg[0, 3, 200]                       # tie: torch.argmax takes the first maximum (150)
+    res, gen, tgt = accuracy(lg, tgt_out, vocab)
+    classes = sorted(set(vocab.token_class_ranges.values()))
+    class_of = np.full(vocab.vocab_size, -1, dtype=np.int32)
+    for idx, c in vocab.token_class_ranges.items():
+        class_of[idx] = classes.index(c)
+    torch.save({"logits": lg, "tgt_out": tgt_out, "classes": classes, "class_of": torch.from_numpy(class_of),
+                "accuracy": {k: float(v) for k, v in res.items()},
+                "first_generated": [vocab.char2index(t) for t in gen], "first_target": [vocab.char2index(t) for t in tgt]},
+               os.path.join(OUT, "metrics_small.pt"))
+
+
+def golden_checkpoint():
+    """A checkpoint file exactly as train.py:967-973 writes it (model + torch.optim.Adam state after
+    two steps), for the load / resume / save compatibility tests."""
+    cfg = dict(d=32, h=2, le=2, ld=2, ff=64, maxlen=96)
+    m = build_ref(seed=21, **cfg)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)                     # train.py:264
+    src, tgt_in, tgt_out, src_pad, tgt_pad = O.synth_batch(2, 24, 16, seed=3)
+    tgt_mask = ref_gen.gen_nopeek_mask(tgt_in.shape[1])[None].repeat(2, 1, 1)
+    loss = None
+    for _ in range(2):
+        opt.zero_grad()
+        logits, _ = m(src, tgt_in, src_pad, tgt_pad, src_pad.clone(), tgt_mask)
+        loss = nn.functional.cross_entropy(logits.reshape(-1, 309), tgt_out.reshape(-1), ignore_index=0)
+        loss.backward()
+        opt.step()
+    # gradients of a third step, and the parameters torch.optim.Adam produces from them (resume parity)
+    opt.zero_grad()
+    logits, _ = m(src, tgt_in, src_pad, tgt_pad, src_pad.clone(), tgt_mask)
+    nn.functional.cross_entropy(logits.reshape(-1, 309), tgt_out.reshape(-1), ignore_index=0).backward()
+    ckpt = {"model_state_dict": {k: v.clone() for k, v in m.state_dict().items()},
+            "optimizer_state_dict": __import__("copy").deepcopy(opt.state_dict()), "epoch": 3, "loss": float(loss)}
+    grads3 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    opt.step()
+    torch.save({"cfg": cfg, "checkpoint": ckpt, "grads_step3": grads3,
+                "params_after_step3": {n: p.detach().clone() for n, p in m.named_parameters()}},
+               os.path.join(OUT, "ckpt_ref_small.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = ref_vocab.WordVocab(0, ["key", "tensile", "density", "polyphony", "occupation"])
@@ -227,5 +290,7 @@ if __name__ == "__main__":
     golden_sampling(v)
     golden_decode(v)
     golden_decode(v, name="decode_greedy_cap.pt", all_controls=(), tracks=(2,), bars=(1,))
+    golden_metrics(v)
+    golden_checkpoint()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

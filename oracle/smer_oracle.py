@@ -470,6 +470,34 @@ def infill_decode(sd, src_ids: np.ndarray, targets: Sequence[str], nhead: int,
 # --------------------------------------------------------------------------------------
 # Training-step arithmetic (train.py:722-786) on the oracle forward, via torch autograd.
 # --------------------------------------------------------------------------------------
+# The 13 target classes of vocab.token_class_ranges (vocab.py:159-300, control list of train.py), sorted by name;
+# ids 0 (pad) and 2 (m_0) have none.  Pinned by tests/golden/metrics_small.pt.
+TOKEN_CLASSES = ("density", "duration", "eos", "key", "occupation", "pitch", "polyphony", "program", "structure",
+                 "tempo", "tensile", "time_signature", "unk")
+
+
+def token_accuracy(logits: torch.Tensor, targets: torch.Tensor, class_of: np.ndarray, classes=TOKEN_CLASSES):
+    """train.py:988-1034 `accuracy()`: argmax (first maximum) of every row against the target, pad targets
+    skipped, accumulated per target class and in total; classes never seen keep the value 0."""
+    lg = logits.reshape(-1, logits.shape[-1]).double().numpy()
+    y = targets.reshape(-1).numpy()
+    am = lg.argmax(axis=1)                                     # numpy, like torch: first occurrence of the maximum
+    correct = {c: 0 for c in classes}
+    seen = {c: 0 for c in classes}
+    correct["total"] = seen["total"] = 0
+    for a, t in zip(am, y):
+        if t == 0:
+            continue
+        k = int(class_of[t])
+        if k >= 0:
+            correct[classes[k]] += int(a == t)
+            seen[classes[k]] += 1
+        correct["total"] += int(a == t)
+        seen["total"] += 1
+    acc = {c: (correct[c] / seen[c] if seen[c] else 0) for c in correct}
+    return acc, correct, seen, am.reshape(targets.shape)
+
+
 def train_step_grads(sd: Dict[str, torch.Tensor], src, tgt_in, tgt_out, src_pad, tgt_pad, nhead, W, C):
     """Returns (loss, {name: grad}) for one batch in eval-mode arithmetic (dropout 0)."""
     leaf = {k: v.detach().clone().requires_grad_(k != "pos_enc.pe") for k, v in sd.items()}

@@ -7,10 +7,10 @@ All arithmetic runs in libsmer_b200.so (hand-written sm_100a CUDA, C ABI in incl
 there is no CPU or eager-PyTorch fallback.
 """
 from .model import ScoreTransformer          # noqa: F401
-from .loss import SmerLoss, loss_tables      # noqa: F401
+from .loss import SmerLoss, SmerAccuracy, loss_tables      # noqa: F401
 from .decode import InfillDecoder            # noqa: F401
 
-__all__ = ["ScoreTransformer", "SmerLoss", "loss_tables", "InfillDecoder", "install_as_reference_modules"]
+__all__ = ["ScoreTransformer", "SmerLoss", "SmerAccuracy", "loss_tables", "InfillDecoder", "install_as_reference_modules"]
 
 
 def install_as_reference_modules() -> None:

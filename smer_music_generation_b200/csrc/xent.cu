@@ -86,6 +86,66 @@ extern "C" int smer_xent_fwd(const float* logits, long long ld, const int64_t* t
   return SMER_OK;
 }
 
+// Token accuracy per target class (train.py:988-1034): warp per row, argmax = FIRST maximum like
+// torch.argmax; counts[c] / counts[ncls + 1 + c] = correct / seen tokens of class c, index ncls = total.
+__global__ void __launch_bounds__(256)
+token_accuracy_kernel(const float* __restrict__ logits, long long ld, const int64_t* __restrict__ tgt,
+                      const int* __restrict__ class_of, int ncls, unsigned long long* __restrict__ counts,
+                      int64_t* __restrict__ argmax_out, long long rows, int V) {
+  __shared__ unsigned int sm[2 * (SMER_ACC_MAX_CLASSES + 1)];
+  const int nslots = 2 * (ncls + 1);
+  for (int i = threadIdx.x; i < nslots; i += blockDim.x) sm[i] = 0u;
+  __syncthreads();
+  int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* x = logits + r * ld;
+    float best = -INFINITY;
+    int bi = V;                                    // NaN-free logits: some index < V always wins
+    for (int c = lane; c < V; c += 32) {
+      float v = x[c];
+      if (v > best) { best = v; bi = c; }          // strictly greater: the lane keeps its first maximum
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, off);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      if (argmax_out) argmax_out[r] = bi;
+      long long y = tgt[r];
+      if (y != 0 && y > 0 && y < V) {              // pad targets are skipped (train.py:1016-1017)
+        unsigned int hit = bi == (int)y ? 1u : 0u;
+        int k = class_of[y];
+        if (k >= 0 && k < ncls) {
+          atomicAdd(&sm[k], hit);
+          atomicAdd(&sm[ncls + 1 + k], 1u);
+        }
+        atomicAdd(&sm[ncls], hit);
+        atomicAdd(&sm[2 * ncls + 1], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nslots; i += blockDim.x)
+    if (sm[i]) atomicAdd(counts + i, (unsigned long long)sm[i]);
+}
+
+extern "C" int smer_token_accuracy(const float* logits, long long ld, const int64_t* targets, const int* class_of,
+                                   int ncls, unsigned long long* counts, int64_t* argmax_out, long long rows, int V,
+                                   void* stream) {
+  SMER_CHECK_ARG(ncls >= 0 && ncls <= SMER_ACC_MAX_CLASSES, "smer_token_accuracy: at most %d classes", SMER_ACC_MAX_CLASSES);
+  if (rows == 0) return SMER_OK;
+  long long blocks = (rows + 7) / 8;
+  long long cap = (long long)smer_num_sms() * 8;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  token_accuracy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, ld, targets, class_of, ncls, counts, argmax_out, rows, V);
+  SMER_CHECK_LAUNCH("smer_token_accuracy");
+  return SMER_OK;
+}
+
 extern "C" int smer_xent_bwd(const float* logits, long long ld, const int64_t* targets, const float* W,
                              const float* lse, const double* sums, void* dlogits, int out_dtype, long long ldo,
                              long long rows, int V, int Vpad, float grad_scale, const float* grad_scale_dev,

@@ -109,3 +109,73 @@ class SmerLoss(nn.Module):
     def forward(self, logits, targets):
         K.require_cuda_device()
         return _XentFn.apply(logits, targets, self.W, self.C, self.cat, self.ncat, self._holder)
+
+
+# ---------------------------------------------------------------------------------------
+# Token accuracy by target class: the metric loop of train.py:988-1034 on the device.
+# ---------------------------------------------------------------------------------------
+# class name, first id, last id (inclusive) of vocab.token_class_ranges (vocab.py:159-300) for the
+# default vocabulary (control list key/tensile/density/polyphony/occupation); ids 0 (pad) and 2 (m_0)
+# have no class.  Pinned against the real WordVocab by tests/golden/metrics_small.pt.
+TOKEN_CLASSES = (
+    ("density", 242, 251), ("duration", 234, 241), ("eos", 1, 1), ("key", 272, 295), ("occupation", 262, 271),
+    ("pitch", 146, 233), ("polyphony", 252, 261), ("program", 18, 145), ("structure", 3, 6), ("tempo", 11, 17),
+    ("tensile", 296, 307), ("time_signature", 7, 10), ("unk", 308, 308),
+)
+
+
+def token_class_table(vocab_size: int = 309) -> torch.Tensor:
+    """class_of[v]: index into TOKEN_CLASSES or -1 (int32, CPU)."""
+    t = torch.full((vocab_size,), -1, dtype=torch.int32)
+    for k, (_, lo, hi) in enumerate(TOKEN_CLASSES):
+        t[lo:min(hi, vocab_size - 1) + 1] = k
+    return t
+
+
+class SmerAccuracy(nn.Module):
+    """acc = SmerAccuracy()(logits (B,T,V) | (N,V), targets): the dict `accuracy(outputs, targets, vocab)[0]`
+    of train.py:988-1034 returns -- per target class and 'total', classes without tokens stay 0 -- from one
+    kernel launch and one small D2H instead of a per-token Python loop with an `.item()` per token.
+    `update()` / `compute()` accumulate over several batches (one D2H at `compute()`);
+    `first_sample_argmax` holds the predicted ids of batch element 0 (the reference's `generated_output`)."""
+
+    def __init__(self, vocab_size: int = 309):
+        super().__init__()
+        self.names = [n for n, _, _ in TOKEN_CLASSES]
+        self.register_buffer("class_of", token_class_table(vocab_size), persistent=False)
+        self.register_buffer("counts", torch.zeros(2 * (len(self.names) + 1), dtype=torch.int64), persistent=False)
+        self.first_sample_argmax: Optional[torch.Tensor] = None
+
+    def reset(self) -> None:
+        self.counts.zero_()
+
+    @torch.no_grad()
+    def update(self, logits: torch.Tensor, targets: torch.Tensor) -> None:
+        K.require_cuda_device()
+        lg = logits.detach()
+        if lg.dtype != torch.float32:
+            lg = lg.float()
+        flat, rows, _ = _rows(lg)
+        tg = targets.reshape(-1).contiguous()
+        if tg.dtype != torch.int64:
+            tg = tg.long()
+        if tg.numel() != rows:
+            raise ValueError("targets do not match the logits rows")
+        am = torch.empty(rows, dtype=torch.int64, device=lg.device)
+        ops.token_accuracy(flat, tg, self.class_of, len(self.names), self.counts, am)
+        per_sample = rows // logits.shape[0] if logits.dim() == 3 else rows
+        self.first_sample_argmax = am[:per_sample]
+
+    def compute(self) -> dict:
+        c = self.counts.cpu().tolist()
+        n = len(self.names)
+        out = {}
+        for k, name in enumerate(self.names + ["total"]):
+            seen = c[n + 1 + k]
+            out[name] = c[k] / seen if seen else 0
+        return out
+
+    def forward(self, logits: torch.Tensor, targets: torch.Tensor) -> dict:
+        self.reset()
+        self.update(logits, targets)
+        return self.compute()

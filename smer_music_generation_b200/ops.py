@@ -244,6 +244,12 @@ ATTN_TC_FWD = True
 ATTN_TC_BWD = True
 
 
+def token_accuracy(logits, targets, class_of, ncls, counts, argmax_out=None):
+    with _Timed("accuracy", float(logits.shape[0] * logits.shape[1] * 4), 1):
+        K.check(K.lib().smer_token_accuracy(_p(logits), logits.stride(0), _p(targets), _p(class_of), ncls, _p(counts),
+                                            _p(argmax_out), logits.shape[0], logits.shape[1], K.stream()), "token_accuracy")
+
+
 def xent_fwd(logits, targets, W, Cw, category, ncat, lse, sums, V):
     with _Timed("xent_fwd", float(logits.shape[0] * V * 4), 1):
         rows = logits.shape[0]

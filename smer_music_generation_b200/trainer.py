@@ -242,7 +242,11 @@ class TrainEngine:
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr) semantics (train.py:264: default betas/eps, no weight decay,
     no amsgrad) with the update done by csrc/elementwise.cu:adam_kernel, one launch per tensor.
-    For the module-API path (`loss.backward(); optim.step()`); TrainEngine uses the flat arena."""
+    For the module-API path (`loss.backward(); optim.step()`); TrainEngine uses the flat arena.
+
+    The per-parameter state has torch.optim.Adam's layout (`step` 0-dim float tensor, `exp_avg` /
+    `exp_avg_sq` shaped like the parameter), so the `optimizer_state_dict` of a reference checkpoint
+    (train.py:967-973) loads into it and its own state_dict loads into torch.optim.Adam (train.py:291-295)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
@@ -256,22 +260,27 @@ class FusedAdam(torch.optim.Optimizer):
                     continue
                 st = self.state[p]
                 if not st:
-                    st["step"] = 0
-                    n = (p.numel() + 3) // 4 * 4
-                    st["exp_avg"] = torch.zeros(n, dtype=torch.float32, device=p.device)
-                    st["exp_avg_sq"] = torch.zeros(n, dtype=torch.float32, device=p.device)
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if not torch.is_tensor(st["step"]):
+                    st["step"] = torch.tensor(float(st["step"]))
                 st["step"] += 1
-                if p.numel() % 4 or not p.is_contiguous() or not p.grad.is_contiguous():
-                    # 309-element fc.bias: run on padded scratch copies
-                    n = st["exp_avg"].numel()
-                    pp = torch.zeros(n, device=p.device)
-                    gg = torch.zeros(n, device=p.device)
-                    pp[: p.numel()].copy_(p.reshape(-1))
-                    gg[: p.numel()].copy_(p.grad.reshape(-1))
-                    ops.adam_step(pp, gg, st["exp_avg"], st["exp_avg_sq"], None, st["step"], g["lr"], g["betas"][0],
-                                  g["betas"][1], g["eps"])
-                    p.copy_(pp[: p.numel()].view(p.shape))
+                step = int(st["step"].item())                 # host tensor (torch's default): no device sync
+                m, v = st["exp_avg"], st["exp_avg_sq"]
+                direct = (p.numel() % 4 == 0 and p.is_contiguous() and p.grad.is_contiguous() and m.is_contiguous()
+                          and v.is_contiguous() and m.dtype == torch.float32 and v.dtype == torch.float32)
+                if direct:
+                    ops.adam_step(p, p.grad, m, v, None, step, g["lr"], g["betas"][0], g["betas"][1], g["eps"])
                 else:
-                    ops.adam_step(p, p.grad, st["exp_avg"], st["exp_avg_sq"], None, st["step"], g["lr"],
-                                  g["betas"][0], g["betas"][1], g["eps"])
+                    # e.g. the 309-element fc.bias: run on scratch copies padded to the kernel's 4-element vectors
+                    n = (p.numel() + 3) // 4 * 4
+                    buf = torch.zeros(4, n, dtype=torch.float32, device=p.device)
+                    for row, t in zip(buf, (p, p.grad, m, v)):
+                        row[: p.numel()].copy_(t.reshape(-1))
+                    ops.adam_step(buf[0], buf[1], buf[2], buf[3], None, step, g["lr"], g["betas"][0], g["betas"][1],
+                                  g["eps"])
+                    p.copy_(buf[0, : p.numel()].view(p.shape))
+                    m.copy_(buf[2, : p.numel()].view(m.shape))
+                    v.copy_(buf[3, : p.numel()].view(v.shape))
         return loss
