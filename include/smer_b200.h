@@ -141,6 +141,16 @@ int smer_token_accuracy(const float* logits, long long ld, const int64_t* target
 /* ---- K11: Adam.  train.py:264,786 ------------------------------------------------------------ */
 int smer_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, int step,
                    float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* the same update for a table of separate tensors in ONE launch (nn.Parameters of the module path):
+ * table_dev is DEVICE memory, any element counts, max_n = the largest n in the table */
+typedef struct smer_adam_tensor {
+  float* p;
+  const float* g;
+  float *m, *v;
+  long long n;
+} smer_adam_tensor;
+int smer_adam_multi(const smer_adam_tensor* table_dev, int n_tensors, long long max_n, int step, float lr, float beta1,
+                    float beta2, float eps, float grad_scale, void* stream);
 /* same update with the step number read from device memory (CUDA-graph replays) */
 int smer_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
                        const uint64_t* step_dev, float lr, float beta1, float beta2, float eps, float grad_scale,

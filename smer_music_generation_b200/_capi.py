@@ -62,6 +62,7 @@ _SIGS = {
     "smer_gemm_bf16_tc": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _f, _u64,
                                _u64, _i, _vp, _vp]),
     "smer_colsum": (_i, [_vp, _i, _ll, _vp, _ll, _i, _vp]),
+    "smer_adam_multi": (_i, [_vp, _i, _ll, _i, _f, _f, _f, _f, _f, _vp]),
     "smer_token_accuracy": (_i, [_vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _i, _vp]),
     "smer_attn_fwd_simt": (_i, [C.POINTER(AttnArgs), _vp]),
     "smer_attn_bwd_simt": (_i, [C.POINTER(AttnArgs), _vp]),

@@ -364,6 +364,58 @@ extern "C" int smer_adam_step(float* p, const float* g, float* m, float* v, void
   return adam_launch(p, g, m, v, bf16_shadow, n, step, nullptr, lr, beta1, beta2, eps, grad_scale, stream);
 }
 
+// Multi-tensor form for ordinary (non-contiguous-arena) nn.Parameters: one launch over a device table of
+// tensors, any element counts (scalar head/tail around the 16-byte-aligned body).  All tensors share `step`.
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const smer_adam_tensor* __restrict__ table, float lr, float b1, float b2, float eps, float bc1,
+                  float bc2_sqrt, float gscale) {
+  const smer_adam_tensor t = table[blockIdx.y];
+  float* __restrict__ p = t.p;
+  const float* __restrict__ g = t.g;
+  float* __restrict__ m = t.m;
+  float* __restrict__ v = t.v;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    const float gk = gg * gscale;
+    mm = b1 * mm + (1.f - b1) * gk;
+    vv = b2 * vv + (1.f - b2) * gk * gk;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pp -= (lr / bc1) * (mm / denom);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? t.n / 4 : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x, tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long i = tid; i < n4; i += stride) {
+    float pp[4], gg[4], mm[4], vv[4];
+    load4(p + i * 4, pp);
+    load4(g + i * 4, gg);
+    load4(m + i * 4, mm);
+    load4(v + i * 4, vv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) upd(pp[k], gg[k], mm[k], vv[k]);
+    store4(p + i * 4, pp);
+    store4(m + i * 4, mm);
+    store4(v + i * 4, vv);
+  }
+  for (long long i = n4 * 4 + tid; i < t.n; i += stride) upd(p[i], g[i], m[i], v[i]);
+}
+
+extern "C" int smer_adam_multi(const smer_adam_tensor* table_dev, int n_tensors, long long max_n, int step, float lr,
+                               float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  SMER_CHECK_ARG(table_dev && n_tensors >= 0 && step >= 1, "smer_adam_multi: bad arguments");
+  if (n_tensors == 0) return SMER_OK;
+  SMER_CHECK_ARG(n_tensors <= 65535, "smer_adam_multi: at most 65535 tensors per launch");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  long long bx = (max_n / 4 + 255) / 256;
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;                        // the largest tensor grid-strides; small ones finish in their first block
+  dim3 grid((unsigned)bx, (unsigned)n_tensors);
+  adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  SMER_CHECK_LAUNCH("smer_adam_multi");
+  return SMER_OK;
+}
+
 extern "C" int smer_adam_step_dev(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n,
                                   const uint64_t* step_dev, float lr, float beta1, float beta2, float eps,
                                   float grad_scale, void* stream) {

@@ -275,6 +275,13 @@ def adam_step(p, g, m, v, shadow, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_sca
                                            grad_scale, K.stream()), "adam_step")
 
 
+def adam_multi(table_dev, n_tensors, max_n, total_n, step, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+    """One launch over a device table of (p, g, m, v, n) entries (40 bytes each, smer_adam_tensor)."""
+    with _Timed("adam", float(total_n * 28), 1):
+        K.check(K.lib().smer_adam_multi(_p(table_dev), n_tensors, max_n, step, lr, b1, b2, eps, grad_scale, K.stream()),
+                "adam_multi")
+
+
 def cast2d(src, dst, cols=None):
     with _Timed("cast", 0.0, 1):
         rows = src.shape[0]

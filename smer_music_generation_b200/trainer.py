@@ -255,32 +255,49 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         for g in self.param_groups:
+            rows, total, max_n, step = [], 0, 0, None
             for p in g["params"]:
                 if p.grad is None:
                     continue
                 st = self.state[p]
                 if not st:
                     st["step"] = torch.tensor(0.0)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 if not torch.is_tensor(st["step"]):
                     st["step"] = torch.tensor(float(st["step"]))
                 st["step"] += 1
-                step = int(st["step"].item())                 # host tensor (torch's default): no device sync
+                this_step = int(st["step"].item())             # host tensor (torch's default): no device sync
                 m, v = st["exp_avg"], st["exp_avg_sq"]
-                direct = (p.numel() % 4 == 0 and p.is_contiguous() and p.grad.is_contiguous() and m.is_contiguous()
-                          and v.is_contiguous() and m.dtype == torch.float32 and v.dtype == torch.float32)
-                if direct:
-                    ops.adam_step(p, p.grad, m, v, None, step, g["lr"], g["betas"][0], g["betas"][1], g["eps"])
-                else:
-                    # e.g. the 309-element fc.bias: run on scratch copies padded to the kernel's 4-element vectors
-                    n = (p.numel() + 3) // 4 * 4
-                    buf = torch.zeros(4, n, dtype=torch.float32, device=p.device)
-                    for row, t in zip(buf, (p, p.grad, m, v)):
-                        row[: p.numel()].copy_(t.reshape(-1))
-                    ops.adam_step(buf[0], buf[1], buf[2], buf[3], None, step, g["lr"], g["betas"][0], g["betas"][1],
-                                  g["eps"])
-                    p.copy_(buf[0, : p.numel()].view(p.shape))
-                    m.copy_(buf[2, : p.numel()].view(m.shape))
-                    v.copy_(buf[3, : p.numel()].view(v.shape))
+                ok = (p.is_contiguous() and p.grad.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+                      and p.dtype == p.grad.dtype == m.dtype == v.dtype == torch.float32)
+                if not ok:
+                    raise RuntimeError("FusedAdam: parameters, gradients and state must be contiguous fp32 tensors")
+                if step is not None and this_step != step:     # one table shares the bias correction: flush per step value
+                    self._launch(rows, total, max_n, step, g)
+                    rows, total, max_n = [], 0, 0
+                step = this_step
+                rows.append((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()))
+                total += p.numel()
+                max_n = max(max_n, p.numel())
+            if rows:
+                self._launch(rows, total, max_n, step, g)
         return loss
+
+    def _launch(self, rows, total, max_n, step, g):
+        """All tensors of a group in one kernel launch: the (p, g, m, v, n) table goes through a pinned staging
+        buffer to the device (gradients are fresh tensors every step, so the table is rebuilt every step)."""
+        n = len(rows)
+        dev = g["params"][0].device
+        if getattr(self, "_tab_n", 0) < n:
+            self._tab_host = torch.empty(n, 5, dtype=torch.int64).pin_memory()
+            self._tab_dev = torch.empty(n, 5, dtype=torch.int64, device=dev)
+            self._tab_n = n
+        ev = getattr(self, "_tab_ev", None)
+        if ev is not None:
+            ev.synchronize()                   # the previous step's table has left the pinned buffer (long ago)
+        self._tab_host[:n].copy_(torch.tensor(rows, dtype=torch.int64))
+        self._tab_dev[:n].copy_(self._tab_host[:n], non_blocking=True)
+        self._tab_ev = torch.cuda.Event()
+        self._tab_ev.record()
+        ops.adam_multi(self._tab_dev, n, max_n, total, step, g["lr"], g["betas"][0], g["betas"][1], g["eps"])
