@@ -63,6 +63,17 @@ __device__ __forceinline__ void st_row_chunk_fwd(uint32_t row_addr, uint32_t rx,
   st_shared_v4(row_addr + ((c16 ^ rx) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                pack_bf16x2(v[6], v[7]));
 }
+// Explicit shared-state-space accesses for the small exchange / constant arrays: through a generic pointer
+// the compiler emits LD.E / ST.E (generic path, long-scoreboard latency) on the per-tile critical path.
+__device__ __forceinline__ float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_v4f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_bwd() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -79,8 +90,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *k_empty = bars + 3, *v_empty = bars + 4,
            *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  float* s_xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 parity][2 halves][128 rows]
-  uint32_t* mask_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 2560);   // bit j: key j masked
+  const uint32_t a_xch = ptx::smem_u32(bars) + 256;       // float [2 parity][2 halves][128 rows]
+  const uint32_t a_mask = ptx::smem_u32(bars) + 2560;     // uint32 [MASK_WORDS], bit j: key j masked
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;     // heavy (late-causal) query tiles first
@@ -173,7 +184,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = (warp - 2) * 32 + lane; j < ntiles * BN; j += 256) {
         const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
         const uint32_t bal = __ballot_sync(0xffffffffu, msk);
-        if (lane == 0) mask_all[j >> 5] = bal;
+        if (lane == 0) sts_u(a_mask + (j >> 5) * 4, bal);
       }
       bar_sync_bwd();
     }
@@ -182,8 +193,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int j0 = t * BN;
       uint32_t mw[2] = {0u, 0u};
       if (use_mask) {
-        mw[0] = mask_all[(j0 >> 5) + hf * 2];
-        mw[1] = mask_all[(j0 >> 5) + hf * 2 + 1];
+        mw[0] = lds_u(a_mask + ((j0 >> 5) + hf * 2) * 4);
+        mw[1] = lds_u(a_mask + ((j0 >> 5) + hf * 2 + 1) * 4);
       }
       if (p.causal && j0 + BN - 1 > i0) {
 #pragma unroll
@@ -222,10 +233,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      float* xch = s_xch + (t & 1) * 256;
-      xch[hf * 128 + r] = mx;
+      const uint32_t xch = a_xch + (t & 1) * 1024;
+      sts_f(xch + (hf * 128 + r) * 4, mx);
       bar_sync_bwd();
-      mx = fmaxf(mx, xch[(hf ^ 1) * 128 + r]);
+      mx = fmaxf(mx, lds_f(xch + ((hf ^ 1) * 128 + r) * 4));
       const float m_new = fmaxf(m, mx * c2);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2(m - m_use);
@@ -311,10 +322,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     // row sum = both halves
-    float* xch = s_xch + (ntiles & 1) * 256;
-    xch[hf * 128 + r] = l;
+    const uint32_t xch = a_xch + (ntiles & 1) * 1024;
+    sts_f(xch + (hf * 128 + r) * 4, l);
     bar_sync_bwd();
-    l += xch[(hf ^ 1) * 128 + r];
+    l += lds_f(xch + ((hf ^ 1) * 128 + r) * 4);
     if (row_ok) {
       const float inv = l > 0.f ? p.inv_keep / l : 0.f;      // dropout's 1/(1-p) applied once per row
       bf16* orow = p.o + ((long long)b * p.Lq + i) * p.ldo + h * DH + hf * 32;
@@ -395,7 +406,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_empty = bars + 3 /*[2]*/, *sp_full = bars + 5 /*[2]*/,
            *ds_full = bars + 7 /*[2]*/, *ds_free = bars + 9 /*[2]*/, *dq_done = bars + 11;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
-  uint32_t* mask_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 1536);   // bit j: key j masked
+  const uint32_t a_mask = ptx::smem_u32(bars) + 1536;     // uint32 [MASK_WORDS], bit j: key j masked
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = gridDim.x - 1 - blockIdx.x;
@@ -516,14 +527,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int j = (warp - 2) * 32 + lane; j < ntiles * BKV; j += 256) {
         const bool msk = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]);
         const uint32_t bal = __ballot_sync(0xffffffffu, msk);
-        if (lane == 0) mask_all[j >> 5] = bal;
+        if (lane == 0) sts_u(a_mask + (j >> 5) * 4, bal);
       }
     }
     {
-      float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // [2][128]
-      xch[hf * 128 + r] = dsum;
+      const uint32_t xch = ptx::smem_u32(bars) + 256;      // float [2][128]
+      sts_f(xch + (hf * 128 + r) * 4, dsum);
       bar_sync_bwd();
-      dsum += xch[(hf ^ 1) * 128 + r];
+      dsum += lds_f(xch + ((hf ^ 1) * 128 + r) * 4);
       if (row_ok && hf == 0) p.dsum[rowid] = dsum;             // for the dK/dV kernel that follows on the stream
     }
     const float c2 = p.c_log2;
@@ -531,7 +542,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int u = 0; u < 2 * ntiles; ++u) {
       const int t = u >> 1, hh = u & 1;
       const int j0 = t * BKV + hh * 32;                // first key of the 32-key sub-tile; this thread: keys j0 + 16hf ...
-      uint32_t w32 = use_mask ? mask_all[j0 >> 5] : 0u;
+      uint32_t w32 = use_mask ? lds_u(a_mask + (j0 >> 5) * 4) : 0u;
       if (p.causal && j0 + 31 > i0) {
         const int nvis = i - j0 + 1;
         w32 |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
@@ -651,9 +662,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *sp_full = bars + 5,
            *pds_full = bars + 6, *done = bars + 7;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
-  float* s_lse = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);      // [2][64], 16-byte aligned
-  float* s_dsum = s_lse + 2 * BKV;                            // [2][64]
-  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_dsum + 2 * BKV);   // [2][64]
+  const uint32_t a_lse = ptx::smem_u32(bars) + 128;        // float [2][64], 16-byte aligned
+  const uint32_t a_dsum = a_lse + 2 * BKV * 4;             // float [2][64]
+  const uint32_t a_key = a_dsum + 2 * BKV * 4;             // uint32 [2][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -752,9 +763,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           ds_ = p.dsum[rowbase + i];
           if (p.thr16) rk = attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (i & ~7));   // key of the 8-row block
         }
-        s_lse[slot + r] = l2;
-        s_dsum[slot + r] = ds_;
-        s_key[slot + r] = rk;
+        sts_f(a_lse + (slot + r) * 4, l2);
+        sts_f(a_dsum + (slot + r) * 4, ds_);
+        sts_u(a_key + (slot + r) * 4, rk);
       }
       bar_sync_bwd();
       const int cm = (p.causal && iq0 < j0 + BM) ? (j - iq0) : 0;       // query columns < cm cannot see key j
@@ -780,12 +791,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
           float pd[8], ds[8];
           // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is 8 steps on
-          uint32_t xk = p.thr16 ? attn_mix(s_key[slot + cb] + jg) * jm + ja : 0u;
+          uint32_t xk = p.thr16 ? attn_mix(lds_u(a_key + (slot + cb) * 4) + jg) * jm + ja : 0u;
 #pragma unroll
           for (int k4 = 0; k4 < 2; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
             const int colb = cb + k4 * 4;
-            const float4 l4 = *reinterpret_cast<const float4*>(s_lse + slot + colb);
-            const float4 d4 = *reinterpret_cast<const float4*>(s_dsum + slot + colb);
+            const float4 l4 = lds_v4f(a_lse + (slot + colb) * 4);
+            const float4 d4 = lds_v4f(a_dsum + (slot + colb) * 4);
             const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
             const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
