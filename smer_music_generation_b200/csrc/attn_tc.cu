@@ -281,12 +281,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               lsum2 = add2(lsum2, pack2(pv[k], pv[k + 1]));
             }
             if (p.thr16) {                               // one mixed word per 8 keys, then one multiply-add per key
-              uint32_t x = attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa;
+              uint32_t x[8];
+              attn_block8<1>(attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa, x);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                pv[k] = x >= p.thr16 ? pv[k] : 0.f;
-                if (k < 7) x = attn_step(x);
-              }
+              for (int k = 0; k < 8; ++k) pv[k] = x[k] >= p.thr16 ? pv[k] : 0.f;
             }
             st_shared_v4(dst, pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
                          pack_bf16x2(pv[6], pv[7]));
@@ -575,7 +573,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               st_shared_v4(dst, 0u, 0u, 0u, 0u);
             } else {
               float ds[8];
-              uint32_t xk = p.thr16 ? attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa : 0u;
+              uint32_t x[8];
+              attn_block8<1>(p.thr16 ? attn_mix(kbase + (uint32_t)c * ATTN_GOLD) * pm + pa : 0u, x);
 #pragma unroll
               for (int k = 0; k < 8; k += 2) {
                 float e0, e1;
@@ -587,10 +586,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 }
                 float d0 = __uint_as_float(dv[c][k]), d1 = __uint_as_float(dv[c][k + 1]);
                 if (p.thr16) {
-                  d0 = xk >= p.thr16 ? d0 : 0.f;
-                  xk = attn_step(xk);
-                  d1 = xk >= p.thr16 ? d1 : 0.f;
-                  if (k != 6) xk = attn_step(xk);
+                  d0 = x[k] >= p.thr16 ? d0 : 0.f;
+                  d1 = x[k + 1] >= p.thr16 ? d1 : 0.f;
                 }
                 // dS = P * (dP * keep/(1-p) - D)
                 unpack2(mul2(pack2(p0, p1), fma2(pack2(d0, d1), ik2, nd2)), ds[k], ds[k + 1]);
@@ -791,7 +788,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
           float pd[8], ds[8];
           // 8 consecutive queries (tile starts are multiples of 8) share one mixed word; each next query is 8 steps on
-          uint32_t xk = p.thr16 ? attn_mix(lds_u(a_key + (slot + cb) * 4) + jg) * jm + ja : 0u;
+          uint32_t x[8];
+          attn_block8<8>(p.thr16 ? attn_mix(lds_u(a_key + (slot + cb) * 4) + jg) * jm + ja : 0u, x);
 #pragma unroll
           for (int k4 = 0; k4 < 2; ++k4) {             // per-query-row constants come as 16-byte broadcast loads
             const int colb = cb + k4 * 4;
@@ -814,9 +812,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
               const f32x2 dd2 = pack2(__uint_as_float(dv[cur][k]), __uint_as_float(dv[cur][k + 1]));
               if (p.thr16) {
                 // kf = keep/(1-p): one select per element serves both P^T*kf (dV operand) and dP*kf
-                const uint32_t x0 = xk, x1 = attn_step8(xk);
-                if (k != 6) xk = attn_step8(x1);
-                const f32x2 kf = pack2(x0 >= p.thr16 ? p.inv_keep : 0.f, x1 >= p.thr16 ? p.inv_keep : 0.f);
+                const f32x2 kf = pack2(x[k] >= p.thr16 ? p.inv_keep : 0.f, x[k + 1] >= p.thr16 ? p.inv_keep : 0.f);
                 unpack2(mul2(pp, kf), pd[k], pd[k + 1]);
                 // dS^T = P * (dP * keep/(1-p) - D)
                 unpack2(mul2(pp, fma2(dd2, kf, pack2(-dd[u], -dd[u + 1]))), ds[k], ds[k + 1]);

@@ -230,6 +230,21 @@ __device__ __forceinline__ uint32_t attn_blk_x(uint32_t blockkey, int j) {
 __device__ __forceinline__ uint32_t attn_step(uint32_t x) { return x * ATTN_A + ATTN_C; }
 __device__ __forceinline__ uint32_t attn_step4(uint32_t x) { return x * ATTN_A4 + ATTN_C4; }
 __device__ __forceinline__ uint32_t attn_step8(uint32_t x) { return x * ATTN_A8 + ATTN_C8; }
+// x[k] = x0 advanced by k*STEP steps, k = 0..7, as a depth-3 tree of multiply-adds (7 IMADs like the serial
+// chain, but a dependency depth of 3 instead of 7)
+template <int STEP>
+__device__ __forceinline__ void attn_block8(uint32_t x0, uint32_t (&x)[8]) {
+  constexpr uint32_t M1 = lcg_mul_n(STEP), A1 = lcg_add_n(STEP), M2 = lcg_mul_n(2 * STEP), A2 = lcg_add_n(2 * STEP),
+                     M4 = lcg_mul_n(4 * STEP), A4 = lcg_add_n(4 * STEP);
+  x[0] = x0;
+  x[1] = x0 * M1 + A1;
+  x[2] = x0 * M2 + A2;
+  x[4] = x0 * M4 + A4;
+  x[3] = x[2] * M1 + A1;
+  x[5] = x[4] * M1 + A1;
+  x[6] = x[4] * M2 + A2;
+  x[7] = x[6] * M1 + A1;
+}
 // n LCG steps as one multiply-add: x -> x * mul + add
 __device__ __forceinline__ void attn_advance(int n, uint32_t& mul, uint32_t& add) {
   mul = 1u; add = 0u;
