@@ -411,6 +411,7 @@ def run_decode(args):
         pieces.append(O.mask_bar_and_track_ids(ids, [0, 1, 2], [4, 5, 6, 7], 3))
         targets.append(O.mask_targets(4, [0, 1, 2], 3))
     dec = InfillDecoder(model, mode="top_p", top_p=0.9, seed=7, max_len=args.decode_len, splits=args.splits)
+    dec.trace_intervals = True                           # device time of every 16-step graph launch (events only)
     res = None
     times, dev_times = [], []
     gens = []
@@ -431,6 +432,7 @@ def run_decode(args):
             dev_times.append(res["device_ms"])          # encoder + cross K/V + graph capture + decode loop
             gens.append(sum(res["generated"]))
     clk = clocks.stop() if clocks else None
+    intervals = [round(x / 16, 3) for x in getattr(dec, "interval_ms", [])]      # of the last timed generate()
     ms = sum(times)
     ms_dev = sum(dev_times)
     toks = float(sum(gens))
@@ -466,6 +468,7 @@ def run_decode(args):
                         "d2h_bytes_per_step": dec.d2h_bytes, "ms_per_step": ms / args.steps},
                 "clocks": clk, "gpu_launches": kl, "decode_steps": res["steps"], "roofline": roof,
                 "step_ms_graph": ms_dev / args.steps / max(1, res["steps"]),
+                "step_ms_by_interval": intervals[:40],
                 "hbm_bytes_per_step_algorithmic": pr["cross"]["bytes"] + pr["self"]["bytes"]}
         print(json.dumps(line), flush=True)
     if world > 1:
