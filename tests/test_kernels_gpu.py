@@ -322,7 +322,8 @@ def test_attention_fwd_bwd(dev, dtype, H, dh, Lq, Lk, causal, use_pad):
 @pytest.mark.parametrize("Lq,Lk,causal,use_pad,drop", [(128, 128, False, False, 0.0), (256, 256, True, False, 0.0),
                                                        (200, 200, True, True, 0.0), (1024, 1024, True, True, 0.0),
                                                        (100, 777, False, True, 0.0), (384, 1024, False, True, 0.1),
-                                                       (512, 512, True, True, 0.1), (1, 130, False, False, 0.0)])
+                                                       (512, 512, True, True, 0.1), (1, 130, False, False, 0.0),
+                                                       (2304, 2304, True, True, 0.1), (640, 2100, False, True, 0.0)])
 def test_attention_tc_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
     """tcgen05 forward == CUDA-core forward on the same bf16 inputs (same dropout mask: both use
     the counter hash of common.cuh) and == torch fp32 when dropout is off."""

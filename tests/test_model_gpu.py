@@ -110,6 +110,33 @@ def test_full_size_forward_vs_oracle(oracle):
         assert relerr(lg[valid], ref[valid]) < tol, mode
 
 
+def test_c5_shape_forward_and_grads_vs_oracle(oracle):
+    """The configs[4] architecture family (d768, 12 heads of 64, ff3072) on sequences longer than one CTA pair's
+    tile and not a multiple of 128, with padding: logits, loss and gradients against the oracle (bf16 tolerances);
+    exercises the d768 LayerNorm fast path, N=2304 / K=768 / K=3072 GEMM shapes and multi-tile attention."""
+    O = oracle
+    cfg = dict(d=768, h=12, le=2, ld=2, ff=3072, maxlen=320)
+    sd = O.random_state_dict(cfg["d"], cfg["h"], cfg["le"], cfg["ld"], cfg["ff"], cfg["maxlen"], seed=4)
+    src, tgt_in, tgt_out, sp, tp = O.synth_batch(3, 300, 280, seed=6)
+    W, C = O.loss_weights(1.0)
+    ref_loss, ref_grads, ref_logits, _ = O.train_step_grads(sd, src, tgt_in, tgt_out, sp, tp, cfg["h"], W, C)
+    from smer_music_generation_b200 import SmerLoss
+    m = _build(cfg, sd, "bf16").train()                      # dropout 0: train == eval arithmetic
+    lg, _ = m(src.to(DEV), tgt_in.to(DEV), sp.to(DEV), tp.to(DEV), sp.to(DEV), "causal")
+    valid = ~tp
+    assert relerr(lg[valid], ref_logits[valid]) < 2e-2
+    loss, _, _ = SmerLoss(309, 1.0).to(DEV)(lg, tgt_out.to(DEV))
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
+    loss.backward()
+    worst = 0.0
+    for n, p in m.named_parameters():
+        g, r = p.grad.detach().cpu().float(), ref_grads[n]
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
+        assert cos > 0.98, (n, cos)
+        worst = max(worst, (g - r).abs().max().item() / max(r.abs().max().item(), 1e-12))
+    assert worst < 0.25, worst
+
+
 def test_dropout_training_statistics(oracle):
     """With dropout on, parity is statistical: outputs differ between calls, stay finite, and the
     mean over many passes approaches the eval-mode output direction (keep-rate scaling is right)."""
