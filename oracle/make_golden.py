@@ -254,6 +254,31 @@ def golden_metrics(vocab):
                os.path.join(OUT, "metrics_small.pt"))
 
 
+def golden_spans(vocab):
+    """generation.mask_bar_and_track (generation.py:248-341) and generation.restore_marked_input
+    (generation.py:417-465) on synthetic pieces, as ids."""
+    cases = []
+    rng = np.random.RandomState(9)
+    for seed, (n_bars, n_tracks, ev) in enumerate([(8, 3, 4), (16, 3, 6), (6, 2, 3), (5, 1, 5)]):
+        ids = O.synth_piece(seed=seed, n_bars=n_bars, n_tracks=n_tracks, events_per_track_bar=ev)
+        events = [vocab.index2char(int(i)) for i in ids]
+        for tracks, bars in [(list(range(n_tracks)), list(range(n_bars // 2, n_bars // 2 + 2))), ([n_tracks - 1], [1]),
+                             ([0], [0, n_bars - 1])]:
+            src, tnames, bnames = ref_gen.mask_bar_and_track(list(events), vocab, tracks, bars)
+            src_tokens = [vocab.index2char(int(i)) for i in src]
+            n_mask = int((np.asarray(src) == vocab.char2index("m_0")).sum())
+            gen = []
+            for k in range(n_mask if seed % 2 == 0 else max(1, n_mask - 1)):      # odd seeds: one span fewer than masks
+                gen.append("m_0")
+                gen.extend(vocab.index2char(int(t)) for t in rng.randint(146, 242, size=rng.randint(0, 6)))
+            restored = ref_gen.restore_marked_input(src_tokens, gen)
+            cases.append({"ids": np.asarray(ids), "tracks": tracks, "bars": bars, "src": np.asarray(src),
+                          "track_names": list(tnames), "bar_names": list(bnames),
+                          "generated": np.asarray([vocab.char2index(t) for t in gen]),
+                          "restored": np.asarray([vocab.char2index(str(t)) for t in restored])})
+    torch.save(cases, os.path.join(OUT, "spans.pt"))
+
+
 def golden_checkpoint():
     """A checkpoint file exactly as train.py:967-973 writes it (model + torch.optim.Adam state after
     two steps), for the load / resume / save compatibility tests."""
@@ -291,6 +316,7 @@ if __name__ == "__main__":
     golden_decode(v)
     golden_decode(v, name="decode_greedy_cap.pt", all_controls=(), tracks=(2,), bars=(1,))
     golden_metrics(v)
+    golden_spans(v)
     golden_checkpoint()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

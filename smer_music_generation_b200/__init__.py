@@ -9,6 +9,7 @@ there is no CPU or eager-PyTorch fallback.
 from .model import ScoreTransformer          # noqa: F401
 from .loss import SmerLoss, SmerAccuracy, loss_tables      # noqa: F401
 from .decode import InfillDecoder            # noqa: F401
+from . import spans                          # noqa: F401
 
 __all__ = ["ScoreTransformer", "SmerLoss", "SmerAccuracy", "loss_tables", "InfillDecoder", "install_as_reference_modules"]
 

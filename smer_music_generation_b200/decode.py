@@ -24,6 +24,7 @@ import torch
 
 from . import _capi as K
 from . import ops
+from . import spans
 
 TARGET_CODES = {"r": 0, "d": 1, "o": 2, "p": 3, "t": 4}
 
@@ -364,6 +365,21 @@ class InfillDecoder:
         return out
 
     # -- public -----------------------------------------------------------------------
+    def infill(self, pieces, tracks_to_generate: Sequence[int], bars_to_generate: Sequence[int], **kw) -> Dict[str, object]:
+        """Whole pieces in, completed pieces out -- the id-level equivalent of generation.generation_all
+        (generation.py:468-702) for a batch: mask the selected (bar, track) spans (spans.mask_bar_and_track),
+        decode all pieces together on the device, put the generated spans back (spans.restore_marked_input).
+        Returns generate()'s dict plus `restored` (list of int64 arrays) and `src` (the masked inputs)."""
+        srcs, targets = [], []
+        for ids in pieces:
+            src, _, _ = spans.mask_bar_and_track(ids, tracks_to_generate, bars_to_generate)
+            srcs.append(src.tolist())
+            targets.append(spans.mask_targets(ids, tracks_to_generate, bars_to_generate))
+        res = self.generate(srcs, targets, **kw)
+        res["src"] = srcs
+        res["restored"] = [spans.restore_marked_input(s, g) for s, g in zip(srcs, res["streams"])]
+        return res
+
     @torch.no_grad()
     def generate(self, pieces, targets, nwd: Optional[Sequence[bool]] = None, seq_base: int = 0, max_steps: int = 0,
                  check_every: int = 16) -> Dict[str, object]:

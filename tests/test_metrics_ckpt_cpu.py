@@ -67,3 +67,27 @@ def test_reference_checkpoint_loads_and_round_trips(golden_dir):
     adam.step()
     for n, p in m2.named_parameters():
         assert torch.allclose(p.detach(), fx["params_after_step3"][n], rtol=0, atol=1e-7), n
+
+
+def test_span_surgery_matches_reference_fixture(golden_dir, oracle):
+    """spans.mask_bar_and_track / restore_marked_input against generation.mask_bar_and_track (generation.py:248-341)
+    and generation.restore_marked_input (generation.py:417-465) run on the reference itself (tests/golden/spans.pt),
+    and against the oracle's id-level restatement on more pieces."""
+    import numpy as np
+    from smer_music_generation_b200 import spans
+    cases = torch.load(os.path.join(golden_dir, "spans.pt"), weights_only=False)
+    assert len(cases) >= 12
+    for c in cases:
+        src, tn, bn = spans.mask_bar_and_track(c["ids"], c["tracks"], c["bars"])
+        assert np.array_equal(src, c["src"]) and tn == c["track_names"] and bn == c["bar_names"]
+        assert np.array_equal(spans.restore_marked_input(src, c["generated"]), c["restored"])
+    for seed in range(6):
+        ids = np.asarray(oracle.synth_piece(seed=seed, n_bars=16, n_tracks=3, events_per_track_bar=6))
+        for tr, br in (([0, 1, 2], [4, 5, 6, 7]), ([2], [15]), ([0, 2], [0, 9])):
+            src, _, _ = spans.mask_bar_and_track(ids, tr, br)
+            assert np.array_equal(src, oracle.mask_bar_and_track_ids(ids, tr, br, 3))
+            assert spans.mask_targets(ids, tr, br) == oracle.mask_targets(len(br), tr, 3)
+    # nothing selected / nothing generated: identity
+    ids = np.asarray(oracle.synth_piece(seed=1, n_bars=4, n_tracks=3, events_per_track_bar=2))
+    assert np.array_equal(spans.mask_bar_and_track(ids, [], [1])[0], ids)
+    assert np.array_equal(spans.restore_marked_input(ids, []), ids)

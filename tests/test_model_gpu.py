@@ -214,6 +214,20 @@ def test_batched_infill_decoder_greedy_ids(golden_dir, oracle, name):
     assert res2["streams"] == res["streams"]
 
 
+@pytest.mark.parametrize("name", ["decode_greedy.pt", "decode_greedy_cap.pt"])
+def test_infill_end_to_end_matches_generation_all(golden_dir, name):
+    """InfillDecoder.infill(whole piece, tracks, bars) == what the reference's generation_all returned for the same
+    piece and selection (greedy): span masking, batched device decode and putting the spans back."""
+    from smer_music_generation_b200 import InfillDecoder
+    g = _load(golden_dir, name)
+    m = _build(g["cfg"], g["state_dict"], "fp32").eval()
+    dec = InfillDecoder(m, mode="greedy", max_len=700, all_controls=g["all_controls"], use_graph=False)
+    res = dec.infill([g["piece_ids"], g["piece_ids"]], g["tracks"], g["bars"])
+    assert res["src"][0] == list(g["src"])
+    for restored in res["restored"]:
+        assert restored.tolist() == list(g["restored"]), name
+
+
 def test_sampled_decode_distribution(oracle):
     """Sampled decode: first-token distribution over 4096 replicas of one piece matches the
     oracle's masked distribution for that state (total variation)."""
