@@ -133,11 +133,40 @@ def cpu_train_step_rate(B, S, T, steps, warmup, threads):
     return ntok * len(times) / sum(times), sum(times) / len(times), ntok
 
 
+def cpu_decode_rate(threads, spans=52):
+    """The reference's decode loop (generation.py:523-687: the whole decoder re-run per token, no KV cache) as
+    restated by the oracle, on ONE configs[3] piece, bounded to `spans` of its 52 masked spans
+    (top-p 0.9 sampling like the GPU arm, spans capped at 24 tokens)."""
+    O = load_oracle()
+    torch.set_num_threads(threads)
+    sd = O.random_state_dict(CFG["d"], CFG["nhead"], CFG["le"], CFG["ld"], CFG["ff"], CFG["max_len"], seed=0)
+    ids = O.synth_piece(seed=0, n_bars=16, n_tracks=3, events_per_track_bar=6)
+    src = O.mask_bar_and_track_ids(ids, [0, 1, 2], [4, 5, 6, 7], 3)
+    targets = O.mask_targets(4, [0, 1, 2], 3)[:spans]
+    t0 = time.perf_counter()
+    import numpy as np
+    tr = O.infill_decode(sd, src, targets, CFG["nhead"], mode="sample", top_p=0.9, rng=np.random.default_rng(7), max_span=24)
+    dt = time.perf_counter() - t0
+    return tr.generated / dt, dt, tr.generated, len(src)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    if args.workload == "decode":
+        rate, sec, ntok, S = cpu_decode_rate(threads)
+        sample = (f"oracle port of generation.py:523-687 (uncached: whole decoder per token), one piece (S={S}), all 52 spans "
+                  f"(<= 24 tokens each, encoder output computed once -- the reference re-encodes per token) = {ntok} tokens in {sec:.1f} s, top-p 0.9, fp32, {threads} torch threads")
+        line = {"impl": "reference", "metric": METRIC_DECODE, "value": rate, "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": 1, "warmup": 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[3]: KV-cached infilling of 1024 pieces", "reference_sample": "one piece, 52 spans, on CPU"},
+                "cpu_baseline": {"value": rate, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": rate, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
     B, S, T = 2, args.seq, args.tgt
     rate, sec, ntok = cpu_train_step_rate(B, S, T, args.steps, min(args.warmup, 1), threads)
     sample = (f"oracle port of train.py:722-786 (fwd+loss+bwd+Adam, fp32, eval-mode arithmetic: no dropout RNG), "
@@ -470,6 +499,13 @@ def run_decode(args):
                 "step_ms_graph": ms_dev / args.steps / max(1, res["steps"]),
                 "step_ms_by_interval": intervals[:40],
                 "hbm_bytes_per_step_algorithmic": pr["cross"]["bytes"] + pr["self"]["bytes"]}
+        line["cpu_baseline"] = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, sec, ntok, S0 = cpu_decode_rate(threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "sample": f"oracle port of generation.py:523-687 (uncached), one piece (S={S0}), 52 spans (encoder hoisted) = "
+                                              f"{ntok} tokens in {sec:.1f} s, top-p 0.9, fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
