@@ -42,15 +42,16 @@ def _encode(model, src, src_pad):
     return mem, run
 
 
-def _cross_kv(model, run, mem):
+def _cross_kv(model, run, mem, out=None):
+    """Per decoder layer the K|V projection of the encoder memory; `out`: persistent buffers to fill."""
     d = model.d_model
-    out = []
+    res = []
     for i, layer in enumerate(model.transformer.decoder.layers):
         ap = model._attn_p(layer.multihead_attn, f"transformer.decoder.layers.{i}.multihead_attn.")
-        kv = torch.empty(mem.shape[0], 2 * d, dtype=model.compute_dtype, device=mem.device)
+        kv = out[i] if out is not None else torch.empty(mem.shape[0], 2 * d, dtype=model.compute_dtype, device=mem.device)
         ops.gemm_nt(mem, ap.w[d:3 * d], kv, bias=ap.b[d:])
-        out.append(kv)
-    return out
+        res.append(kv)
+    return res
 
 
 # ----------------------------------------------------------------------------------------
@@ -212,55 +213,45 @@ class InfillDecoder:
         self.profile = None                 # list of (kind, start, end) CUDA events when profiling one eager step
 
     # -- state ------------------------------------------------------------------------
-    def _setup(self, pieces, targets, nwd, seq_base):
+    def _weight_ptrs(self):
+        """Addresses of every weight tensor the captured step reads (bf16 shadows are re-made when weights change)."""
+        ptrs = []
+        for lp in self.layer_p:
+            for ap in (lp.sa, lp.ca):
+                ptrs += [ap.w.data_ptr(), ap.b.data_ptr(), ap.wo.data_ptr(), ap.bo.data_ptr()]
+            ptrs += [lp.w1.data_ptr(), lp.b1.data_ptr(), lp.w2.data_ptr(), lp.b2.data_ptr()]
+            ptrs += [t.data_ptr() for pair in lp.ln for t in pair]
+        ptrs += [t.data_ptr() for t in self.fc_p]
+        return tuple(ptrs)
+
+    def _alloc(self, n, S, max_spans, dev):
+        """Device buffers of one problem shape.  They persist across generate() calls of the same shape so that the
+        captured CUDA graph (which bakes their addresses) can be replayed without being re-captured."""
         m = self.m
-        dev = m.embedding.weight.device
-        n = len(pieces)
         d, H = m.d_model, m.nhead
-        lens = np.fromiter((len(p) for p in pieces), dtype=np.int64, count=n)
-        S = (int(lens.max()) + 7) // 8 * 8
-        src_np = np.zeros((n, S), dtype=np.int64)
-        flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in pieces])
-        cols = np.arange(S)[None, :] < lens[:, None]               # valid positions, row-major == concat order
-        src_np[cols] = flat
-        src = torch.from_numpy(src_np)
-        pad = torch.from_numpy(~cols)
-        self.h2d_bytes = src.numel() * 8 + pad.numel()
-        src = src.pin_memory().to(dev, non_blocking=True)
-        pad_u8 = pad.to(torch.uint8).pin_memory().to(dev, non_blocking=True)
-        self.n, self.S, self.dev = n, S, dev
-        self.src_len = torch.from_numpy(lens.astype(np.int32)).to(dev)
-        self._ev0 = torch.cuda.Event(enable_timing=True)
-        self._ev0.record()                                        # device work starts here (encoder)
-        mem, run = _encode(m, src, pad_u8)
-        self.cross = _cross_kv(m, run, mem)
-        del mem, run
         nl = len(m.transformer.decoder.layers)
         dt = m.compute_dtype
         L = self.max_len
+        self.n, self.S, self.dev, self.max_spans = n, S, dev, max_spans
+        self.src_dev = torch.zeros(n, S, dtype=torch.int64, device=dev)
+        self.pad_dev = torch.zeros(n, S, dtype=torch.uint8, device=dev)
+        self.src_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.cross = [torch.empty(n * S, 2 * d, dtype=dt, device=dev) for _ in range(nl)]
         self.self_kv = [torch.zeros(n, L, 2 * d, dtype=dt, device=dev) for _ in range(nl)]
-        nsp = np.fromiter((len(t) for t in targets), dtype=np.int64, count=n)
-        max_spans = int(nsp.max())
-        tg_np = np.zeros((n, max_spans), dtype=np.int8)
-        codes = np.fromiter((TARGET_CODES[c] for t in targets for c in t), dtype=np.int8, count=int(nsp.sum()))
-        tg_np[np.arange(max_spans)[None, :] < nsp[:, None]] = codes
-        self.max_spans = max_spans
-        self.targets = torch.from_numpy(tg_np).to(dev)
-        self.n_spans = torch.from_numpy(nsp.astype(np.int32)).to(dev)
-        self.nwd = torch.tensor([1 if x else 0 for x in nwd], dtype=torch.uint8).to(dev)
+        self.targets = torch.zeros(n, max_spans, dtype=torch.int8, device=dev)
+        self.n_spans = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.nwd = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.tok_buf = torch.zeros(n, L, dtype=torch.int64, device=dev)
-        self.tok_buf[:, 0] = 2                                     # every stream opens with m_0
         self.cur_len = torch.ones(n, dtype=torch.int32, device=dev)
         self.fed_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self.span_start = torch.zeros(n, dtype=torch.int32, device=dev)
         self.span_idx = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.done = (self.n_spans == 0).to(torch.int32)
+        self.done = torch.zeros(n, dtype=torch.int32, device=dev)
         self.gen_count = torch.zeros(n, dtype=torch.int32, device=dev)
         self.state = torch.zeros(n, dtype=torch.int32, device=dev)
         self.bitmap = torch.from_numpy(self.control_bitmap_host.view(np.int32).copy()).to(dev)
         self.ids = torch.zeros(n, dtype=torch.int64, device=dev)
         self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.seq_base = seq_base
         ws = K.lib().smer_decode_attn_workspace_bytes(n, H, d // H, self.splits)
         self.ws = torch.empty(max(ws, 4) // 4, dtype=torch.float32, device=dev)
         # static activation buffers (graph-capturable step)
@@ -268,9 +259,53 @@ class InfillDecoder:
         mk = lambda c, t=None: torch.empty(n, c, dtype=t or dt, device=dev)
         self.buf = dict(x=mk(d), qkv=mk(3 * d), o=mk(d), proj=mk(d), y1=mk(d), z=mk(d), q2=mk(d), o2=mk(d), y2=mk(d),
                         h=mk(ff), f=mk(d), y3=mk(d), yo=mk(d), logits=mk(m.vpad, torch.float32))
+        self.graph = None
+
+    def _setup(self, pieces, targets, nwd, seq_base):
+        m = self.m
+        dev = m.embedding.weight.device
+        n = len(pieces)
+        lens = np.fromiter((len(p) for p in pieces), dtype=np.int64, count=n)
+        S = (int(lens.max()) + 7) // 8 * 8
+        src_np = np.zeros((n, S), dtype=np.int64)
+        flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in pieces])
+        cols = np.arange(S)[None, :] < lens[:, None]               # valid positions, row-major == concat order
+        src_np[cols] = flat
+        nsp = np.fromiter((len(t) for t in targets), dtype=np.int64, count=n)
+        max_spans = max(1, int(nsp.max()))
+        tg_np = np.zeros((n, max_spans), dtype=np.int8)
+        codes = np.fromiter((TARGET_CODES[c] for t in targets for c in t), dtype=np.int8, count=int(nsp.sum()))
+        tg_np[np.arange(max_spans)[None, :] < nsp[:, None]] = codes
         self.layer_p = [m._layer_p(l, f"transformer.decoder.layers.{i}.") for i, l in enumerate(m.transformer.decoder.layers)]
         self.fc_p = m._fc_p()
-        self.graph = None
+        key = (n, S, max_spans, self.max_len, seq_base, str(dev), self.mode, self.temperature, self.top_p, self.top_k,
+               self.seed, self.splits, self._weight_ptrs())
+        if getattr(self, "_key", None) != key:
+            self._alloc(n, S, max_spans, dev)
+            self._key = key
+        self.seq_base = seq_base
+        src = torch.from_numpy(src_np).pin_memory()
+        pad = torch.from_numpy((~cols).astype(np.uint8)).pin_memory()
+        self.h2d_bytes = src.numel() * 8 + pad.numel()
+        self.src_dev.copy_(src, non_blocking=True)
+        self.pad_dev.copy_(pad, non_blocking=True)
+        self.src_len.copy_(torch.from_numpy(lens.astype(np.int32)))
+        self._ev0 = torch.cuda.Event(enable_timing=True)
+        self._ev0.record()                                        # device work starts here (encoder)
+        mem, run = _encode(m, self.src_dev, self.pad_dev)
+        _cross_kv(m, run, mem, out=self.cross)
+        del mem, run
+        for kv in self.self_kv:
+            kv.zero_()
+        self.targets.copy_(torch.from_numpy(tg_np))
+        self.n_spans.copy_(torch.from_numpy(nsp.astype(np.int32)))
+        self.nwd.copy_(torch.tensor([1 if x else 0 for x in nwd], dtype=torch.uint8))
+        self.tok_buf.zero_()
+        self.tok_buf[:, 0] = 2                                     # every stream opens with m_0
+        self.cur_len.fill_(1)
+        for t in (self.fed_len, self.span_start, self.span_idx, self.gen_count, self.state, self.ids, self.pos):
+            t.zero_()
+        self.done.copy_((self.n_spans == 0).to(torch.int32))
 
     def _decode_attn(self, q, new_k, new_v, kc, vc, out, kv_len, key_pad, ld_cache, cache_stride, cache_len, ld_pad):
         m = self.m
@@ -390,7 +425,10 @@ class InfillDecoder:
         self._setup(pieces, targets, nwd, seq_base)
         max_steps = max_steps or self.max_len
         steps = 0
-        if self.use_graph:
+        if not self.use_graph:
+            self.graph = None
+        elif self.graph is None or getattr(self, "_graph_steps", 0) != check_every:
+            # (the graph is kept across generate() calls: same buffers, same weights -> same graph)
             # warm up once on a side stream (lazy module loads are not capturable), restore the state
             snap = [t.clone() for t in (self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx,
                                         self.done, self.gen_count, self.state)]
@@ -410,6 +448,7 @@ class InfillDecoder:
             with torch.cuda.graph(self.graph):
                 for _ in range(check_every):
                     self._step(0)
+            self._graph_steps = check_every
             for t, c in zip((self.tok_buf, self.cur_len, self.fed_len, self.span_start, self.span_idx, self.done,
                              self.gen_count, self.state), snap):
                 t.copy_(c)
