@@ -491,7 +491,8 @@ def run_decode(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": f"configs[3]: {n_total} independent 16-bar pieces (S<={S}), 4 bars x 3 tracks masked "
                                        f"(52 spans), KV cache, grammar-masked top-p 0.9 sampling, stream cap {args.decode_len}",
-                           "timed": "value: pieces resident on the device -> encoder, cross-KV, decode loop (CUDA events); "
+                           "timed": "value: pieces resident on the device -> encoder, cross-KV, decode loop (CUDA events; the 16-step CUDA graph is "
+                                    "captured in the warm-up call and replayed by the timed calls: same shapes, same weights); "
                                     "e2e: whole InfillDecoder.generate() incl. host packing, H2D, D2H of the token streams"},
                 "e2e": {"value": toks / (ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": dec.h2d_bytes,
                         "d2h_bytes_per_step": dec.d2h_bytes, "ms_per_step": ms / args.steps},
