@@ -48,6 +48,7 @@ struct FwdParams {
   float inv_keep;
   uint64_t seed, site;
   const unsigned long long* seed_dev;
+  int nq, items;           // persistent forward: query tiles per (b,h), nq * H * B work items
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -77,6 +78,7 @@ __device__ __forceinline__ void sts_u(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_bwd() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+template <bool PERSIST>      // PERSIST: CTAs walk several work items; otherwise one item per CTA (the loops below run once)
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, FwdParams p) {
@@ -88,24 +90,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sP = smem + 3 * TILE_QKV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_QKV + TILE_P);
   uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *k_empty = bars + 3, *v_empty = bars + 4,
-           *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+           *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7, *q_empty = bars + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
   const uint32_t a_xch = ptx::smem_u32(bars) + 256;       // float [2 parity][2 halves][128 rows]
   const uint32_t a_mask = ptx::smem_u32(bars) + 2560;     // uint32 [MASK_WORDS], bit j: key j masked
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;     // heavy (late-causal) query tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int i0 = qt * BM;
-  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
-  if (p.causal) kend = min(kend, i0 + BM);
-  const int ntiles = (kend + BN - 1) / BN;
+  // Persistent CTA: work items (query tile, head, batch row), heaviest (late-causal) query tiles first, dealt
+  // round-robin to the resident CTAs.  Barrier phases run on across items: `gt` counts KV tiles, `qi` counts
+  // items that had any, identically in every role.
+  const int HB = p.H * p.B;
+  auto item_of = [&](int item, int& b, int& h, int& i0, int& kend, int& ntiles) {
+    // causal: all (b,h) of the heaviest query tile first; full: the query tiles of one (b,h) next to each other
+    // (they share K/V through L2 while they run together)
+    const int qt = p.causal ? p.nq - 1 - item / HB : item % p.nq;
+    const int rem = p.causal ? item % HB : item / p.nq;
+    h = rem % p.H;
+    b = rem / p.H;
+    i0 = qt * BM;
+    kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+    if (p.causal) kend = min(kend, i0 + BM);
+    ntiles = (kend + BN - 1) / BN;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(bars + i, i == 6 ? 256 : 1);
+    for (int i = 0; i < 9; ++i) ptx::mbar_init(bars + i, i == 6 ? 256 : 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -116,17 +128,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     if (ptx::elect_one()) {
-      if (ntiles > 0) {
+      uint32_t gt = 0, qi = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int b, h, i0, kend, ntiles;
+        item_of(item, b, h, i0, kend, ntiles);
+        if (ntiles == 0) continue;
+        if (qi > 0) ptx::mbar_wait(q_empty, (qi - 1) & 1);        // the previous item's S MMAs have read sQ
         ptx::mbar_expect_tx(q_full, TILE_QKV);
         ptx::tma_load_2d(sQ, &tmQ, q_full, h * DH, b * p.Lq + i0);
-      }
-      for (int t = 0; t < ntiles; ++t) {
-        if (t > 0) ptx::mbar_wait(k_empty, (t - 1) & 1);
-        ptx::mbar_expect_tx(k_full, TILE_QKV);
-        ptx::tma_load_2d(sK, &tmK, k_full, h * DH, b * p.Lk + t * BN);
-        if (t > 0) ptx::mbar_wait(v_empty, (t - 1) & 1);
-        ptx::mbar_expect_tx(v_full, TILE_QKV);
-        ptx::tma_load_2d(sV, &tmV, v_full, h * DH, b * p.Lk + t * BN);
+        for (int t = 0; t < ntiles; ++t, ++gt) {
+          if (gt > 0) ptx::mbar_wait(k_empty, (gt - 1) & 1);
+          ptx::mbar_expect_tx(k_full, TILE_QKV);
+          ptx::tma_load_2d(sK, &tmK, k_full, h * DH, b * p.Lk + t * BN);
+          if (gt > 0) ptx::mbar_wait(v_empty, (gt - 1) & 1);
+          ptx::mbar_expect_tx(v_full, TILE_QKV);
+          ptx::tma_load_2d(sV, &tmV, v_full, h * DH, b * p.Lk + t * BN);
+        }
+        ++qi;
+        if (!PERSIST) break;
       }
     }
     __syncwarp();
@@ -135,9 +154,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
       const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV), aP = ptx::smem_u32(sP);
-      if (ntiles > 0) ptx::mbar_wait(q_full, 0);
-      for (int t = 0; t < ntiles; ++t) {
-        ptx::mbar_wait(k_full, t & 1);
+      uint32_t gt = 0, qi = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, h, i0, kend, ntiles;
+      item_of(item, b, h, i0, kend, ntiles);
+      if (ntiles == 0) continue;
+      ptx::mbar_wait(q_full, qi & 1);
+      for (int t = 0; t < ntiles; ++t, ++gt) {
+        ptx::mbar_wait(k_full, gt & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
@@ -145,8 +169,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             idesc_s, k > 0 ? 1u : 0u);
         ptx::umma_commit(k_empty);
         ptx::umma_commit(s_full);
-        ptx::mbar_wait(p_full, t & 1);
-        ptx::mbar_wait(v_full, t & 1);
+        if (t == ntiles - 1) ptx::umma_commit(q_empty);          // last S of the item: sQ may be refilled
+        ptx::mbar_wait(p_full, gt & 1);
+        ptx::mbar_wait(v_full, gt & 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
@@ -157,12 +182,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::umma_commit(v_empty);
         ptx::umma_commit(o_full);
       }
+      ++qi;
+      if (!PERSIST) break;
+      }
     }
     __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int hf = (warp - 2) >> 2;              // keys [hf*64, hf*64+64) of every tile, output columns [hf*32, hf*32+32)
     const int r = quarter * 32 + lane;
+    uint32_t gt = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    int b, h, i0, kend, ntiles;
+    item_of(item, b, h, i0, kend, ntiles);
     const int i = i0 + r;
     const bool row_ok = i < p.Lq;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -178,7 +210,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-    // key-mask bitmap of all the tiles this CTA visits, built once (one barrier instead of one per tile)
+    // key-mask bitmap of all the tiles of this item, built once (one barrier per item instead of one per tile;
+    // the barrier also separates this item's exchange buffers from the previous item's last read)
     const bool use_mask = p.pad != nullptr || (kend & (BN - 1)) != 0;
     if (use_mask) {
       for (int j = (warp - 2) * 32 + lane; j < ntiles * BN; j += 256) {
@@ -186,10 +219,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t bal = __ballot_sync(0xffffffffu, msk);
         if (lane == 0) sts_u(a_mask + (j >> 5) * 4, bal);
       }
-      bar_sync_bwd();
     }
+    bar_sync_bwd();
 
-    for (int t = 0; t < ntiles; ++t) {
+    for (int t = 0; t < ntiles; ++t, ++gt) {
       const int j0 = t * BN;
       uint32_t mw[2] = {0u, 0u};
       if (use_mask) {
@@ -203,7 +236,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mw[c] |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
         }
       }
-      ptx::mbar_wait(s_full, t & 1);
+      ptx::mbar_wait(s_full, gt & 1);
       ptx::tc_fence_after();
       // ---- pass 1: maximum of this thread's 64 visible scores, then the row maximum via smem
       float mx = -INFINITY;
@@ -233,7 +266,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      const uint32_t xch = a_xch + (t & 1) * 1024;
+      const uint32_t xch = a_xch + (gt & 1) * 1024;
       sts_f(xch + (hf * 128 + r) * 4, mx);
       bar_sync_bwd();
       mx = fmaxf(mx, lds_f(xch + ((hf ^ 1) * 128 + r) * 4));
@@ -307,7 +340,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tc_fence_before();            // orders this thread's tcgen05.ld before the next MMAs
       ptx::mbar_arrive(p_full);
       // ---- O += P V  (rescale the running accumulator, add the tile result): this thread's 32 columns
-      ptx::mbar_wait(o_full, t & 1);
+      ptx::mbar_wait(o_full, gt & 1);
       ptx::tc_fence_after();
       {
         uint32_t v[32];
@@ -320,7 +353,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
     // row sum = both halves
-    const uint32_t xch = a_xch + (ntiles & 1) * 1024;
+    const uint32_t xch = a_xch + (gt & 1) * 1024;
     sts_f(xch + (hf * 128 + r) * 4, l);
     bar_sync_bwd();
     l += lds_f(xch + ((hf ^ 1) * 128 + r) * 4);
@@ -339,6 +372,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (p.lse && hf == 0)
         p.lse[((long long)b * p.H + h) * p.Lq + i] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
     }
+    if (!PERSIST) break;
+    }   // items
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -913,11 +948,23 @@ extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   static bool attr_set = false;
   if (!attr_set) {
-    SMER_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    SMER_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    SMER_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
     attr_set = true;
   }
-  dim3 grid((a->Lq + BM - 1) / BM, a->H, a->B);
-  attn_fwd_tc_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  p.nq = (a->Lq + BM - 1) / BM;
+  const long long items = (long long)p.nq * a->H * a->B;
+  SMER_CHECK_ARG(items < (1ll << 31), "smer_attn_fwd_tc: too many work items");
+  p.items = (int)items;
+  // Causal: persistent CTAs (two per SM) walking the items heaviest-first -- the per-CTA set-up (TMEM allocation,
+  // barrier init, first loads) is paid once instead of once per 1..8-tile item: 136 -> 127 us at B32 x 1024^2.
+  // Full attention: one item per CTA; there the hardware's dynamic block scheduling balances the kv_len-dependent
+  // item lengths better than a static round-robin (184 vs 196 us).
+  const long long slots = 2ll * smer_num_sms();
+  if (a->causal && items > slots)
+    attn_fwd_tc_kernel<true><<<dim3((unsigned)slots), FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  else
+    attn_fwd_tc_kernel<false><<<dim3((unsigned)items), FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   SMER_CHECK_LAUNCH("smer_attn_fwd_tc");
   return SMER_OK;
 }
