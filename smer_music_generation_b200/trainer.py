@@ -293,11 +293,14 @@ class FusedAdam(torch.optim.Optimizer):
             self._tab_host = torch.empty(n, 5, dtype=torch.int64).pin_memory()
             self._tab_dev = torch.empty(n, 5, dtype=torch.int64, device=dev)
             self._tab_n = n
-        ev = getattr(self, "_tab_ev", None)
-        if ev is not None:
-            ev.synchronize()                   # the previous step's table has left the pinned buffer (long ago)
-        self._tab_host[:n].copy_(torch.tensor(rows, dtype=torch.int64))
-        self._tab_dev[:n].copy_(self._tab_host[:n], non_blocking=True)
-        self._tab_ev = torch.cuda.Event()
-        self._tab_ev.record()
+            self._tab_rows = None
+        if rows != getattr(self, "_tab_rows", None):       # the caching allocator usually hands the gradients the same
+            ev = getattr(self, "_tab_ev", None)             # addresses every step: then the device table is still valid
+            if ev is not None:
+                ev.synchronize()               # the previous table has left the pinned buffer (long ago)
+            self._tab_host[:n].copy_(torch.tensor(rows, dtype=torch.int64))
+            self._tab_dev[:n].copy_(self._tab_host[:n], non_blocking=True)
+            self._tab_ev = torch.cuda.Event()
+            self._tab_ev.record()
+            self._tab_rows = rows
         ops.adam_multi(self._tab_dev, n, max_n, total, step, g["lr"], g["betas"][0], g["betas"][1], g["eps"])
