@@ -124,6 +124,9 @@ int smer_attn_weights(const smer_attn_args* a, float* weights, long long ldw, vo
 /* sums[0]=sum W[y]*nll, sums[1]=sum C[y], sums[2+k]=category k numerator (DEVICE doubles) */
 int smer_xent_fwd(const float* logits, long long ld, const int64_t* targets, const float* W, const float* C,
                   const int* category, int ncat, float* lse, double* sums, long long rows, int V, void* stream);
+/* sums[1] = sum_i C[y_i] only (the other SMER_XENT_MAX_SUMS entries are zeroed): the normaliser depends on the
+ * targets alone, so data-parallel steps reduce it across ranks before the forward pass has finished */
+int smer_xent_denominator(const int64_t* targets, const float* C, double* sums, long long rows, int V, void* stream);
 int smer_xent_bwd(const float* logits, long long ld, const int64_t* targets, const float* W, const float* lse,
                   const double* sums, void* dlogits, int out_dtype, long long ldo, long long rows, int V,
                   int Vpad, float grad_scale, const float* grad_scale_dev /* device scalar or NULL */,
@@ -206,6 +209,10 @@ typedef struct smer_sample_args {
   /* outputs */
   int64_t* out_token;         /* [n_seq] or NULL                                              */
   double* out_probs;          /* [n_seq, V] final sampling distribution, or NULL              */
+  double* trace_masked;       /* [n_seq, max_len, V] or NULL: the masked softmax (before nucleus / top-k) of every
+                                 sampling step, stored at the stream position of the token just fed -- parity
+                                 instrumentation for "sampled decode matches the per-step masked distributions" */
+  int* trace_span;            /* [n_seq, max_len] or NULL: the span index that sampling step belonged to        */
 } smer_sample_args;
 int smer_sample_masked(const smer_sample_args* a, void* stream);
 

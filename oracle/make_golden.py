@@ -179,10 +179,16 @@ def golden_sampling(vocab):
     np.savez_compressed(os.path.join(OUT, "sampling.npz"), **res)
 
 
-def golden_decode(vocab, name="decode_greedy.pt", all_controls=tuple(range(242, 308)), tracks=(1, 2), bars=(1, 2)):
+def golden_decode(vocab, name="decode_greedy.pt", all_controls=tuple(range(242, 308)), tracks=(1, 2), bars=(1, 2),
+                  time_sig=7, model_seed=21):
     cfg = dict(d=32, h=2, le=2, ld=2, ff=64, maxlen=700)
-    m = build_ref(seed=21, **cfg).eval()
-    ids = O.synth_piece(seed=3, n_bars=4, n_tracks=3, events_per_track_bar=3)
+    m = build_ref(seed=model_seed, **cfg).eval()
+    if time_sig != 7:
+        # make the whole-note token (id 234) the likeliest continuation wherever the grammar allows it, so that the
+        # no_whole_duration rule of generation.py:504-507 decides tokens of the greedy stream
+        with torch.no_grad():
+            m.fc.bias[234] += 6.0
+    ids = O.synth_piece(seed=3, n_bars=4, n_tracks=3, events_per_track_bar=3, time_sig=time_sig)
     events = [vocab.index2char(i) for i in ids]
     steps = []
     orig_mg, orig_ws = ref_gen.model_generate, ref_gen.weighted_sampling
@@ -310,11 +316,18 @@ def golden_checkpoint():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     v = ref_vocab.WordVocab(0, ["key", "tensile", "density", "polyphony", "occupation"])
+    if "--nwd-only" in sys.argv:         # just the fixtures added for the no_whole_duration rule
+        golden_decode(v, name="decode_greedy_34.pt", tracks=(0, 2), bars=(1,), time_sig=8)
+        golden_decode(v, name="decode_greedy_68.pt", tracks=(1,), bars=(2,), time_sig=10)
+        sys.exit(0)
     golden_vocab(v)
     golden_forward(v)
     golden_sampling(v)
     golden_decode(v)
     golden_decode(v, name="decode_greedy_cap.pt", all_controls=(), tracks=(2,), bars=(1,))
+    # 3/4 and 6/8 pieces: no_whole_duration = True (generation.py:504-507)
+    golden_decode(v, name="decode_greedy_34.pt", tracks=(0, 2), bars=(1,), time_sig=8)
+    golden_decode(v, name="decode_greedy_68.pt", tracks=(1,), bars=(2,), time_sig=10)
     golden_metrics(v)
     golden_spans(v)
     golden_checkpoint()

@@ -522,13 +522,14 @@ def adam_step(p, g, m, v, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
 # --------------------------------------------------------------------------------------
 # Synthetic SMER pieces -- used by tests and bench on both arms.
 # --------------------------------------------------------------------------------------
-def synth_piece(seed: int = 0, n_bars: int = 16, n_tracks: int = 3, events_per_track_bar: int = 4) -> List[int]:
+def synth_piece(seed: int = 0, n_bars: int = 16, n_tracks: int = 3, events_per_track_bar: int = 4,
+                time_sig: int = 7) -> List[int]:
     """Control-mode-2 layout (encode.py:559-804): header [ts, tempo, key, d*N, o*N, y*N, i*N];
     per bar `bar, s_*`; per track `track_n, d,o,y, <notes>, d,o,y`; trailing s_* after the
     last track of each bar."""
     import random
     r = random.Random(seed)
-    ids = [7, 14, 272]
+    ids = [time_sig, 14, 272]          # time signature ids 7..10 = '4/4', '3/4', '2/4', '6/8' (vocab.py:26)
     ids += [DENSITY.start + r.randrange(10) for _ in range(n_tracks)]
     ids += [OCCUPATION.start + r.randrange(10) for _ in range(n_tracks)]
     ids += [POLYPHONY.start + r.randrange(10) for _ in range(n_tracks)]

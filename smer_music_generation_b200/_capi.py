@@ -45,7 +45,7 @@ class SampleArgs(C.Structure):
                 ("state", _vp), ("targets", _vp), ("nwd", _vp), ("max_spans", _i), ("raw_flags", _vp),
                 ("raw_only_lo", _vp), ("raw_only_hi", _vp), ("tok_buf", _vp), ("cur_len", _vp), ("span_start", _vp),
                 ("span_idx", _vp), ("fed_len", _vp), ("n_spans", _vp), ("done", _vp), ("gen_count", _vp), ("control_bitmap", _vp),
-                ("max_len", _i), ("max_span", _i), ("out_token", _vp), ("out_probs", _vp)]
+                ("max_len", _i), ("max_span", _i), ("out_token", _vp), ("out_probs", _vp), ("trace_masked", _vp), ("trace_span", _vp)]
 
 
 _SIGS = {
@@ -70,6 +70,7 @@ _SIGS = {
     "smer_attn_bwd_tc": (_i, [C.POINTER(AttnArgs), _vp]),
     "smer_attn_weights": (_i, [C.POINTER(AttnArgs), _vp, _ll, _vp]),
     "smer_xent_fwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _i, _vp, _vp, _ll, _i, _vp]),
+    "smer_xent_denominator": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "smer_xent_bwd": (_i, [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _f, _vp, _vp]),
     "smer_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _f, _f, _f, _f, _vp]),
     "smer_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _f, _vp]),

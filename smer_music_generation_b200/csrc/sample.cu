@@ -144,6 +144,9 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
   __syncthreads();
   for (int i = tid; i < V; i += 128) q[i] = q[i] / tot;
   __syncthreads();
+  if (a.trace_masked && pos < a.max_len)
+    for (int i = tid; i < V; i += 128) a.trace_masked[((long long)s * a.max_len + pos) * V + i] = q[i];
+  if (a.trace_span && pos < a.max_len && tid == 0) a.trace_span[(long long)s * a.max_len + pos] = a.span_idx ? a.span_idx[s] : 0;
 
   if (a.mode == SMER_SAMPLE_TOP_P || a.mode == SMER_SAMPLE_TOP_K) {
     // rank by probability, descending; ties resolved towards the higher id (what reversing an
@@ -254,7 +257,11 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
       int gen = a.gen_count[s] + 1;
       bool end_span = false;
       bool is_ctrl = a.control_bitmap && ((a.control_bitmap[idx >> 5] >> (idx & 31)) & 1u);
-      if (is_ctrl) {
+      if (len >= a.max_len) {
+        // the stream buffer is full: the token is dropped and the piece ends here (never write past the row)
+        a.done[s] = 1;
+        gen -= 1;
+      } else if (is_ctrl) {
         buf[len++] = idx;            // kept; the forced <eos> is the element that gets dropped
         gen += 1;
         end_span = true;
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
       } else {
         buf[len++] = idx;
       }
-      if (end_span) {
+      if (end_span && !a.done[s]) {
         int si = a.span_idx[s] + 1;
         st = 0;
         if (si < a.n_spans[s] && len + 1 < a.max_len) {

@@ -86,6 +86,40 @@ extern "C" int smer_xent_fwd(const float* logits, long long ld, const int64_t* t
   return SMER_OK;
 }
 
+// Loss normaliser alone: sums[1] = sum_i C[y_i] (train.py:736).  It depends on the targets only, so under data
+// parallelism it is computed and all-reduced at the START of the step, off the critical path, and the loss backward
+// reads the batch-global value without waiting for a collective after the forward pass.
+__global__ void __launch_bounds__(256)
+xent_denominator_kernel(const int64_t* __restrict__ tgt, const float* __restrict__ C, double* __restrict__ sums,
+                        long long rows, int V) {
+  double acc = 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const long long y = tgt[r];
+    if (y > 0 && y < V) acc += (double)C[y];
+  }
+  acc = warp_sum(acc);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    if (t != 0.0) atomicAdd(sums + 1, t);
+  }
+}
+
+extern "C" int smer_xent_denominator(const int64_t* targets, const float* C, double* sums, long long rows, int V,
+                                     void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SMER_CUDA(cudaMemsetAsync(sums, 0, SMER_XENT_MAX_SUMS * sizeof(double), st));
+  if (rows == 0) return SMER_OK;
+  long long blocks = (rows + 1023) / 1024;
+  int grid = (int)(blocks < 64 ? blocks : 64);
+  xent_denominator_kernel<<<grid, 256, 0, st>>>(targets, C, sums, rows, V);
+  SMER_CHECK_LAUNCH("smer_xent_denominator");
+  return SMER_OK;
+}
+
 // Token accuracy per target class (train.py:988-1034): warp per row, argmax = FIRST maximum like
 // torch.argmax; counts[c] / counts[ncls + 1 + c] = correct / seen tokens of class c, index ncls = total.
 __global__ void __launch_bounds__(256)

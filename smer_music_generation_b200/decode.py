@@ -197,6 +197,10 @@ class InfillDecoder:
                  seed: int = 0, max_len: int = 1024, max_span: int = 100,
                  all_controls: Sequence[int] = tuple(range(242, 308)), splits: int = 1, use_graph: bool = True):
         K.require_cuda_device()
+        if int(max_len) > model.pos_enc.pe.shape[0]:
+            raise ValueError(f"max_len {max_len} exceeds the model's positional table ({model.pos_enc.pe.shape[0]} rows)")
+        if int(max_len) < 2:
+            raise ValueError("max_len must be at least 2")
         self.m = model
         self.mode = {"greedy": K.SAMPLE_GREEDY, "multinomial": K.SAMPLE_MULTINOMIAL, "top_p": K.SAMPLE_TOP_P,
                      "top_k": K.SAMPLE_TOP_K}[mode]
@@ -208,6 +212,8 @@ class InfillDecoder:
         for c in all_controls:
             bm[c >> 5] |= np.uint32(1 << (c & 31))
         self.control_bitmap_host = bm
+        self.trace_distributions = False    # parity instrumentation: keep every step's masked softmax (n, max_len, V) fp64
+        self.trace_masked = None
         self.steps_run = 0
         self.kernel_launches = 0
         self.profile = None                 # list of (kind, start, end) CUDA events when profiling one eager step
@@ -306,6 +312,13 @@ class InfillDecoder:
         for t in (self.fed_len, self.span_start, self.span_idx, self.gen_count, self.state, self.ids, self.pos):
             t.zero_()
         self.done.copy_((self.n_spans == 0).to(torch.int32))
+        if self.trace_distributions:
+            self.trace_masked = torch.zeros(n, self.max_len, m.vocab_size, dtype=torch.float64, device=dev)
+            self.trace_span = torch.full((n, self.max_len), -1, dtype=torch.int32, device=dev)
+            self.graph = None                                 # the trace buffer's address is baked into a captured step
+        elif self.trace_masked is not None:
+            self.trace_masked = None
+            self.graph = None
 
     def _decode_attn(self, q, new_k, new_v, kc, vc, out, kv_len, key_pad, ld_cache, cache_stride, cache_len, ld_pad):
         m = self.m
@@ -375,6 +388,8 @@ class InfillDecoder:
         a.done, a.gen_count, a.control_bitmap = self.done.data_ptr(), self.gen_count.data_ptr(), self.bitmap.data_ptr()
         a.max_len, a.max_span = L, self.max_span
         a.out_token = a.out_probs = None
+        a.trace_masked = self.trace_masked.data_ptr() if self.trace_masked is not None else None
+        a.trace_span = self.trace_span.data_ptr() if self.trace_masked is not None else None
         K.check(lib.smer_sample_masked(C.byref(a), K.stream()), "sample_masked")
         self.launches_per_step = launches + 3
 
@@ -405,11 +420,13 @@ class InfillDecoder:
         (generation.py:468-702) for a batch: mask the selected (bar, track) spans (spans.mask_bar_and_track),
         decode all pieces together on the device, put the generated spans back (spans.restore_marked_input).
         Returns generate()'s dict plus `restored` (list of int64 arrays) and `src` (the masked inputs)."""
-        srcs, targets = [], []
+        srcs, targets, nwd = [], [], []
         for ids in pieces:
             src, _, _ = spans.mask_bar_and_track(ids, tracks_to_generate, bars_to_generate)
             srcs.append(src.tolist())
             targets.append(spans.mask_targets(ids, tracks_to_generate, bars_to_generate))
+            nwd.append(spans.no_whole_duration(ids))
+        kw.setdefault("nwd", nwd)
         res = self.generate(srcs, targets, **kw)
         res["src"] = srcs
         res["restored"] = [spans.restore_marked_input(s, g) for s, g in zip(srcs, res["streams"])]

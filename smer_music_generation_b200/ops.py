@@ -257,6 +257,11 @@ def xent_fwd(logits, targets, W, Cw, category, ncat, lse, sums, V):
                                       _p(lse), _p(sums), rows, V, K.stream()), "xent_fwd")
 
 
+def xent_denominator(targets, Cw, sums, V):
+    with _Timed("xent_fwd", 0.0, 1):
+        K.check(K.lib().smer_xent_denominator(_p(targets), _p(Cw), _p(sums), targets.numel(), V, K.stream()), "xent_denominator")
+
+
 def xent_bwd(logits, targets, W, lse, sums, dlogits, V, grad_scale=1.0, grad_scale_dev=None):
     with _Timed("xent_bwd", float(logits.shape[0] * V * (4 + dlogits.element_size())), 1):
         rows = logits.shape[0]

@@ -19,6 +19,15 @@ TENSILE_LO, TENSILE_HI = 296, 307
 TRACK_CONTROLS = 3                      # density, occupation, polyphony after every track's notes (control mode 2)
 
 
+TIME_SIG_4_4 = 7                        # vocab.py:26: time_signature_token = ['4/4', '3/4', '2/4', '6/8'] -> ids 7..10
+
+
+def no_whole_duration(ids) -> bool:
+    """generation.py:504-507: a whole note is allowed only when the piece's time signature (its first token) is
+    N/4 with N >= 4 -- of the vocabulary's four signatures that is '4/4' alone."""
+    return int(np.asarray(ids).reshape(-1)[0]) != TIME_SIG_4_4
+
+
 def _track_count(ids: np.ndarray) -> int:
     present = np.unique(ids[(ids >= TRACK0) & (ids < TRACK0 + N_TRACK_TOKENS)])
     return int(present.size)

@@ -25,6 +25,9 @@ from .loss import CATEGORIES, CONTROL_NAMES, loss_tables
 from .model import GradArena, ScoreTransformer, _Run
 
 
+_SEED_OWNER = [None]        # id() of the TrainEngine whose step counter the library's seed pointer refers to
+
+
 class ParamArena:
     """Re-homes the module's parameters into one flat fp32 buffer with GradArena's layout (the
     Parameters stay the same objects, so state_dict / checkpoints are unchanged) and keeps flat
@@ -55,6 +58,8 @@ class ParamArena:
             ext["fc.bias"] = self.flat[o:o + vpad]
         model._w.external = ext
         self.refresh_shadow()
+        # model.load_state_dict() copies into the arena views in place: the bf16 shadows must follow
+        model.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_shadow())
 
     def refresh_shadow(self):
         if self.shadow is not None:
@@ -79,11 +84,23 @@ class GradBuckets:
         groups += ["embedding."]
         self.groups = groups
         spans = {g: arena.span(g) for g in groups}
-        per = max(1, math.ceil(len(groups) / max(1, n_buckets)))
-        self.buckets = []
-        for i in range(0, len(groups), per):
-            chunk = groups[i:i + per]
-            self.buckets.append((chunk, min(spans[g][0] for g in chunk), max(spans[g][1] for g in chunk)))
+        if n_buckets and n_buckets > 0:
+            per = max(1, math.ceil(len(groups) / n_buckets))
+            chunks = [groups[i:i + per] for i in range(0, len(groups), per)]
+        else:
+            # default: one bucket per layer (a few MB each, launched the moment that layer's backward is done); the two
+            # stack norms ride with the group signalled next; the embedding table (V x d, the only gradient that is
+            # final at the very end of backward) is ALONE in the last bucket, so the exposed tail is its 0.6 MB
+            chunks, pending = [], []
+            for g in groups[:-1]:
+                pending.append(g)
+                if "layers." in g:
+                    chunks.append(pending)
+                    pending = []
+            if pending:
+                chunks.append(pending)
+            chunks.append([groups[-1]])
+        self.buckets = [(c, min(spans[g][0] for g in c), max(spans[g][1] for g in c)) for c in chunks]
         self.reset()
 
     def reset(self):
@@ -116,7 +133,7 @@ class GradBuckets:
 class TrainEngine:
     def __init__(self, model: ScoreTransformer, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  eos_weight: float = 0.8, control_list: Sequence[str] = CONTROL_NAMES, process_group=None,
-                 n_buckets: int = 4):
+                 n_buckets: int = 0):
         K.require_cuda_device()
         self.model = model
         self.dev = model.embedding.weight.device
@@ -129,6 +146,7 @@ class TrainEngine:
         self.W, self.C, self.cat = W.to(self.dev), C.to(self.dev), cat.to(self.dev)
         self.ncat = len(CATEGORIES)
         self.sums = torch.zeros(K.XENT_MAX_SUMS, dtype=torch.float64, device=self.dev)
+        self.denom = torch.zeros(K.XENT_MAX_SUMS, dtype=torch.float64, device=self.dev)   # [1] = batch-global sum C[y]
         self.step_count = 0
         self.pg = process_group
         self.world = 1
@@ -156,17 +174,28 @@ class TrainEngine:
         T = tgt_in.shape[1]
         pad_s = None if src_pad is None else src_pad.to(torch.uint8)
         pad_t = None if tgt_pad is None else tgt_pad.to(torch.uint8)
-        run = _Run(m, src, tgt_in, pad_s, pad_t, pad_s, True, None, True, seed, False)
-        logits = run.forward(save=True)                              # (B*T, vpad) fp32
         V, vp = m.vocab_size, m.vpad
         tg = tgt_out.reshape(-1)
+        dp = self.world > 1
+        if dp:
+            # The normaliser sum_i C[y_i] (train.py:736) needs only the targets: compute it now and all-reduce it on
+            # the communication stream while the forward pass runs, so the loss backward never waits for a collective
+            import torch.distributed as dist
+            ops.xent_denominator(tg, self.C, self.denom, V)
+            self._on_comm(lambda: dist.all_reduce(self.denom, op=dist.ReduceOp.SUM, group=self.pg))
+        run = _Run(m, src, tgt_in, pad_s, pad_t, pad_s, True, None, True, seed, False)
+        logits = run.forward(save=True)                              # (B*T, vpad) fp32
         lse = torch.empty(B * T, dtype=torch.float32, device=self.dev)
         ops.xent_fwd(logits, tg, self.W, self.C, self.cat, self.ncat, lse, self.sums, V)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.pg)     # global normaliser
         dl = torch.empty(B * T, vp, dtype=m.compute_dtype, device=self.dev)
-        ops.xent_bwd(logits, tg, self.W, lse, self.sums, dl, V, 1.0)
+        if dp:
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_event(self._denom_ready)
+            ops.xent_bwd(logits, tg, self.W, lse, self.denom, dl, V, 1.0)
+            # the numerators (loss value and the per-category terms that get logged) are reduced off the critical path
+            self._on_comm(lambda: dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.pg), record=False)
+        else:
+            ops.xent_bwd(logits, tg, self.W, lse, self.sums, dl, V, 1.0)
         self.grads.flat.zero_()
         if self.buckets is not None:
             self.buckets.reset()
@@ -181,6 +210,21 @@ class TrainEngine:
             a = self.arena
             ops.adam_step(a.flat, self.grads.flat, a.m, a.v, a.shadow, self.step_count, self.lr, self.betas[0],
                           self.betas[1], self.eps, 1.0, step_dev=step_dev)
+
+    def _on_comm(self, fn, record=True):
+        """Runs a collective on the communication stream after everything enqueued so far on the current stream
+        (inline when there is no side stream: gloo / CPU tests).  record: remember its completion in `_denom_ready`."""
+        if self.comm_stream is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            fn()
+            if record:
+                self._denom_ready = torch.cuda.Event()
+                self._denom_ready.record(self.comm_stream)
 
     # ---- the same step captured once into a CUDA graph ---------------------------------
     def capture(self, B: int, S: int, T: int):
@@ -198,16 +242,22 @@ class TrainEngine:
         gi["src"].fill_(3); gi["tgt_in"].fill_(3); gi["tgt_out"].fill_(3)
         self._ctr = torch.full((1,), self.step_count, dtype=torch.int64, device=dev)
         K.check(K.lib().smer_set_seed_device_ptr(self._ctr.data_ptr()), "set_seed_device_ptr")
+        _SEED_OWNER[0] = id(self)
         self._seed_base = (torch.initial_seed() * 0x9E3779B97F4A7C15
                            + (0 if self.pg is None else 7919 * torch.distributed.get_rank(self.pg))) & 0xFFFFFFFFFFFFFFFF
         # warm-up outside capture (lazy kernel loads, cudaFuncSetAttribute), on a side stream
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self._ctr.add_(1)
-            self.step_count += 1
-            self._step_impl(gi["src"], gi["tgt_in"], gi["tgt_out"], gi["src_pad"], gi["tgt_pad"], self._seed_base, True,
+            # forward/loss/backward on the dummy batch WITHOUT the update, and the Adam kernel on scratch buffers:
+            # capture() must leave parameters, moments, shadows and the step counter exactly as it found them
+            self._step_impl(gi["src"], gi["tgt_in"], gi["tgt_out"], gi["src_pad"], gi["tgt_pad"], self._seed_base, False,
                             self._ctr)
+            scratch = [torch.zeros(1024, dtype=torch.float32, device=dev) for _ in range(4)]
+            sh = torch.zeros(1024, dtype=torch.bfloat16, device=dev) if self.arena.shadow is not None else None
+            one = torch.ones(1, dtype=torch.int64, device=dev)
+            ops.adam_step(scratch[0], scratch[1], scratch[2], scratch[3], sh, 1, self.lr, self.betas[0], self.betas[1],
+                          self.eps, 1.0, step_dev=one)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
@@ -232,7 +282,61 @@ class TrainEngine:
 
     def release_graph(self):
         self._graph = None
-        K.lib().smer_set_seed_device_ptr(None)
+        if _SEED_OWNER[0] == id(self):
+            K.lib().smer_set_seed_device_ptr(None)
+            _SEED_OWNER[0] = None
+
+    def __del__(self):
+        # the library keeps the address of `_ctr` (smer_set_seed_device_ptr): never leave it dangling
+        try:
+            if _SEED_OWNER[0] == id(self):
+                K.lib().smer_set_seed_device_ptr(None)
+                _SEED_OWNER[0] = None
+        except Exception:
+            pass
+
+    # ---- optimizer state in torch.optim.Adam's layout (train.py:967-973 checkpoints) -------
+    def _param_order(self):
+        return [(n, p) for n, p in self.model.named_parameters()]
+
+    def optimizer_state_dict(self) -> dict:
+        """The flat-arena Adam state as `torch.optim.Adam(model.parameters(), lr).state_dict()` would hold it:
+        loads into torch.optim.Adam / FusedAdam and is what train.py:970-973 saves as `optimizer_state_dict`."""
+        opt = torch.optim.Adam([p for _, p in self._param_order()], lr=self.lr, betas=self.betas, eps=self.eps)
+        lay = self.arena.layout
+        for n, p in self._param_order():
+            o, _ = lay.offsets[n]
+            k = p.numel()
+            opt.state[p] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.arena.m[o:o + k].view(p.shape).clone(),
+                            "exp_avg_sq": self.arena.v[o:o + k].view(p.shape).clone()}
+        return opt.state_dict()
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Inverse of optimizer_state_dict(); also accepts the `optimizer_state_dict` of a reference checkpoint."""
+        params = self._param_order()
+        opt = torch.optim.Adam([p for _, p in params], lr=self.lr, betas=self.betas, eps=self.eps)
+        opt.load_state_dict(sd)
+        lay = self.arena.layout
+        steps = set()
+        self.arena.m.zero_()
+        self.arena.v.zero_()
+        for n, p in params:
+            st = opt.state.get(p)
+            if not st:
+                continue
+            o, _ = lay.offsets[n]
+            k = p.numel()
+            self.arena.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+            self.arena.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise RuntimeError(f"TrainEngine keeps ONE Adam step number; the state dict holds {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+        g = opt.param_groups[0]
+        self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
+        if getattr(self, "_ctr", None) is not None:
+            self._ctr.fill_(self.step_count)
 
     def loss_value(self) -> float:
         s = self.sums.tolist()
@@ -255,7 +359,7 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         for g in self.param_groups:
-            rows, total, max_n, step = [], 0, 0, None
+            rows, total, max_n, step, touched = [], 0, 0, None, []
             for p in g["params"]:
                 if p.grad is None:
                     continue
@@ -278,10 +382,15 @@ class FusedAdam(torch.optim.Optimizer):
                     rows, total, max_n = [], 0, 0
                 step = this_step
                 rows.append((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()))
+                touched.append(p)
                 total += p.numel()
                 max_n = max(max_n, p.numel())
             if rows:
                 self._launch(rows, total, max_n, step, g)
+            if touched:
+                # The kernel wrote through raw pointers: tell autograd (and everything keyed on `_version`: the bf16
+                # weight shadows of model._Weights, the decode cache stamp) that the parameters changed in place.
+                torch.autograd.graph.increment_version(touched)
         return loss
 
     def _launch(self, rows, total, max_n, step, g):

@@ -31,12 +31,19 @@ def _worker(rank, world, port, q):
         torch.manual_seed(0)
         m = ScoreTransformer(309, 32, 2, 2, 2, 64, 64, 0.0, 0.0)
         arena = GradArena(m)
-        gb = GradBuckets(m, arena, 4, dist.group.WORLD, comm_stream=None)
-        # every arena element belongs to exactly one bucket
-        cover = torch.zeros(arena.total, dtype=torch.int32)
-        for _, b, e in gb.buckets:
-            cover[b:e] += 1
-        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        # default layout: one bucket per layer, the embedding table alone in the last one (the exposed tail)
+        gd = GradBuckets(m, arena, 0, dist.group.WORLD, comm_stream=None)
+        assert gd.buckets[-1][0] == ["embedding."] and len(gd.buckets) == 2 + 2 + 1
+        assert gd.buckets[0][0] == ["fc.", "transformer.decoder.norm.", "transformer.decoder.layers.1."]
+        b_emb, e_emb = gd.buckets[-1][1:]
+        assert e_emb - b_emb == (309 * 32 + 63) // 64 * 64
+        for gb in (gd, GradBuckets(m, arena, 4, dist.group.WORLD, comm_stream=None)):
+            # every arena element belongs to exactly one bucket
+            cover = torch.zeros(arena.total, dtype=torch.int32)
+            for _, b, e in gb.buckets:
+                cover[b:e] += 1
+            assert int(cover.min()) == 1 and int(cover.max()) == 1
+        gb = gd
         # rank-dependent gradients, signalled in the order _Run.backward signals them
         for n, v in arena.views.items():
             v.fill_(float(rank + 1))

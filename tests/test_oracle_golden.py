@@ -129,15 +129,16 @@ def test_state_flags_match_appendix_counts(oracle):
     assert O.allowed_mask(s.flags(2, "r", True)[0]).sum() == 165
 
 
-@pytest.mark.parametrize("name", ["decode_greedy.pt", "decode_greedy_cap.pt"])
+@pytest.mark.parametrize("name", ["decode_greedy.pt", "decode_greedy_cap.pt", "decode_greedy_34.pt", "decode_greedy_68.pt"])
 def test_greedy_decode_matches_reference(oracle, golden_dir, name):
     g = _load(golden_dir, name)
     O = oracle
     src = O.mask_bar_and_track_ids(g["piece_ids"], g["tracks"], g["bars"], 3)
     assert np.array_equal(src, g["src"])
     targets = O.mask_targets(len(g["bars"]), g["tracks"], 3)
+    nwd = int(g["piece_ids"][0]) != 7          # generation.py:504-507: only N/4 with N >= 4 allows the whole note
     tr = O.infill_decode(g["state_dict"], src, targets, g["cfg"]["h"], all_controls=g["all_controls"],
-                         nwd=False, mode="greedy", keep_trace=True)
+                         nwd=nwd, mode="greedy", keep_trace=True)
     assert len(tr.step_logits) == len(g["step_logits"])
     for i, (pref, row) in enumerate(zip(g["step_prefix"], g["step_logits"])):
         assert tr.step_prefix_len[i] == len(pref)
