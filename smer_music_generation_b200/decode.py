@@ -470,10 +470,13 @@ class InfillDecoder:
                              self.gen_count, self.state), snap):
                 t.copy_(c)
         trace = [] if getattr(self, "trace_intervals", False) else None     # diagnostics: device time per check interval
-        while steps < max_steps:
+        live_hist, live = [], n - int(self.done.sum().item())
+        self.check_every_used = check_every
+        while steps < max_steps and live > 0:
             if trace is not None:
                 trace.append(torch.cuda.Event(enable_timing=True))
                 trace[-1].record()
+            live_hist.append(live)
             if self.graph is not None:
                 self.graph.replay()
                 steps += check_every
@@ -481,8 +484,8 @@ class InfillDecoder:
                 for _ in range(check_every):
                     self._step(steps)
                     steps += 1
-            if bool(self.done.all().item()):           # one small D2H every `check_every` tokens
-                break
+            live = n - int(self.done.sum().item())     # one small D2H every `check_every` tokens
+        self.interval_live = live_hist
         self.steps_run = steps
         self.kernel_launches = steps * self.launches_per_step
         ev1 = torch.cuda.Event(enable_timing=True)

@@ -302,15 +302,15 @@ def test_stream_cap_never_overruns(oracle):
     positional table are never touched (sample.cu bookkeeping), every piece ends `done`."""
     from smer_music_generation_b200 import InfillDecoder
     O = oracle
-    sd = O.random_state_dict(32, 2, 1, 1, 64, 64, seed=4)
-    cfg = dict(d=32, h=2, le=1, ld=1, ff=64, maxlen=64)
+    sd = O.random_state_dict(32, 2, 1, 1, 64, 256, seed=4)
+    cfg = dict(d=32, h=2, le=1, ld=1, ff=64, maxlen=256)
     m = _build(cfg, sd, "fp32").eval()
-    piece = O.mask_bar_and_track_ids(O.synth_piece(seed=1, n_bars=2, n_tracks=3, events_per_track_bar=2), [0, 1, 2], [0, 1], 3)
-    targets = O.mask_targets(2, [0, 1, 2], 3)
+    piece = O.mask_bar_and_track_ids(O.synth_piece(seed=1, n_bars=2, n_tracks=3, events_per_track_bar=2), [0, 1, 2], [0], 3)
+    targets = O.mask_targets(1, [0, 1, 2], 3)
     with pytest.raises(ValueError):
-        InfillDecoder(m, max_len=65)
+        InfillDecoder(m, max_len=257)
     for L in (7, 16, 33):
-        dec = InfillDecoder(m, mode="multinomial", max_len=L, seed=3, use_graph=False, all_controls=())
+        dec = InfillDecoder(m, mode="multinomial", max_len=L, seed=3, use_graph=False, all_controls=(), max_span=12)
         res = dec.generate([piece] * 6, [targets] * 6)
         assert all(res["done"])
         lens = [len(s_) for s_ in res["streams"]]
@@ -318,8 +318,8 @@ def test_stream_cap_never_overruns(oracle):
         assert int(dec.cur_len.max().item()) <= L
         for s_ in res["streams"]:
             assert s_[0] == 2                          # every row still opens with its own m_0
-        full = O.infill_decode(sd, piece, targets, 2, all_controls=(), mode="sample", rng=np.random.default_rng(0))
-        assert len(full.tokens) > 33                   # the uncapped stream is longer than every cap tried
+    full = O.infill_decode(sd, piece, targets, 2, all_controls=(), mode="sample", rng=np.random.default_rng(0), max_span=12)
+    assert len(full.tokens) > 33                       # the uncapped stream is longer than every cap tried
 
 
 def test_top_k_keeps_k_largest_and_renormalises(oracle):
@@ -453,9 +453,11 @@ def test_bf16_full_size_s1024_logits_loss_grads_vs_oracle(oracle):
     loss, _, _ = SmerLoss(309, 0.8).to(DEV)(lg, tgt_out.to(DEV))
     assert abs(loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
     loss.backward()
+    bad = {}
     for n, p in m.named_parameters():
         g, r = p.grad.detach().cpu().float(), ref_grads[n]
         cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
-        assert cos > 0.999, (n, cos)
         err = (g - r).abs().max().item() / max(r.abs().max().item(), 1e-12)
-        assert err < 0.1, (n, err)
+        if cos <= 0.999 or err >= 0.1:
+            bad[n] = (round(cos, 5), round(err, 4))
+    assert not bad, bad
