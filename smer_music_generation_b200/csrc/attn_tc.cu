@@ -15,6 +15,7 @@
 //               reads; O accumulated in fp32 registers with the online-softmax rescale.
 //   Two CTAs share an SM (80 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the
 //   other's MMAs.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -929,10 +930,14 @@ int check_common(const smer_attn_args* a, const char* who) {
 
 }  // namespace
 
+int smer_attn_fwd2_launch(const smer_attn_args* a, void* stream);      // attn_fwd2.cu
+
 extern "C" int smer_attn_fwd_tc(const smer_attn_args* a, void* stream) {
   int rc = check_common(a, "smer_attn_fwd_tc");
   if (rc) return rc;
   SMER_CHECK_ARG(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "smer_attn_fwd_tc: o must be 16-byte aligned rows");
+  static const bool use_v1 = getenv("SMER_ATTN_FWD_V1") != nullptr;      // A/B aid: the first-generation kernel below
+  if (!use_v1) return smer_attn_fwd2_launch(a, stream);
   CUtensorMap tq, tk, tv;
   const long long dcols = (long long)a->H * DH;
   if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, (long long)a->B * a->Lq, a->ldq, DH, BM))) return rc;
