@@ -112,6 +112,8 @@ typedef struct smer_attn_args {
   float scale;                /* 1/sqrt(dh)                                                   */
   float dropout_p;
   uint64_t seed, site;
+  void* dq_accum;             /* backward (tc kernels): fp32 [B*Lq, H*dh] workspace; the fused backward accumulates the
+                                 unscaled dQ of all key tiles here (it is zeroed by the call) before converting to dq */
 } smer_attn_args;
 int smer_attn_fwd_simt(const smer_attn_args* a, void* stream);
 int smer_attn_bwd_simt(const smer_attn_args* a, void* stream);

@@ -18,7 +18,7 @@ for step in "$@"; do
   echo "=== [$n] $step"
   case $kind in
     tests)
-      if [ -n "$arg" ]; then timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 -p no:cacheprovider -k "$arg" > gpurun_out/tests_$n.log 2>&1
+      if [ -n "$arg" ]; then timeout ${TLIMIT:-300} python -m pytest tests -m gpu -q -x --timeout 200 -p no:cacheprovider -k "$arg" > gpurun_out/tests_$n.log 2>&1
       else timeout 1800 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/tests_$n.log 2>&1; fi
       echo "rc=$?"; tail -n 40 gpurun_out/tests_$n.log ;;
     smoke)
@@ -27,7 +27,7 @@ for step in "$@"; do
       timeout 1500 python bench.py ${arg//,/ } > gpurun_out/bench_$n.json 2> gpurun_out/bench_$n.log
       echo "rc=$?"; tail -c 1500 gpurun_out/bench_$n.log; tail -c 6000 gpurun_out/bench_$n.json ;;
     prof)
-      timeout 600 python scripts/prof_kernels.py $arg > gpurun_out/prof_${arg:-all}.log 2>&1; echo "rc=$?"; tail -n 40 gpurun_out/prof_${arg:-all}.log ;;
+      timeout 120 python scripts/prof_kernels.py $arg > gpurun_out/prof_${arg:-all}.log 2>&1; echo "rc=$?"; tail -n 40 gpurun_out/prof_${arg:-all}.log ;;
     ab)
       for i in 1 2; do
         echo "== A (old)"; SMER_B200_LIB=$PWD/_ab/libsmer_b200_A.so timeout 300 python scripts/prof_kernels.py $arg 2>&1 | tail -n 24
@@ -46,6 +46,22 @@ for step in "$@"; do
           python scripts/prof_kernels.py $filter > gpurun_out/ncu_$n.log 2>&1
         echo "ncu rc=$?"; tail -n 3 gpurun_out/ncu_$n.log; ls -la gpurun_out/ncu_$n.ncu-rep
       else echo "plain run failed"; tail -n 20 gpurun_out/plain_$n.log; fi ;;
+    ncuq)
+      # quick counters (one or two replay passes): ncuq:REGEX:FILTER[:N]
+      IFS=: read -r regex filter count <<< "$arg"
+      timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,sm__cycles_elapsed.max \
+        --clock-control none -k regex:"$regex" -c ${count:-8} --csv --log-file gpurun_out/ncuq_$n.csv python scripts/prof_kernels.py $filter > gpurun_out/ncuq_$n.log 2>&1
+      echo "ncu rc=$?"; python - <<PYEOF
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/ncuq_$n.csv")) if len(r)>10]
+hdr=rows[0]; ix={h:i for i,h in enumerate(hdr)}
+cur=None
+for r in rows[1:]:
+    key=(r[ix["ID"]], r[ix["Kernel Name"]][:48])
+    if key!=cur: print("==", key); cur=key
+    print("    %-70s %s" % (r[ix["Metric Name"]], r[ix["Metric Value"]]))
+PYEOF
+      ;;
     memcheck)
       timeout 1500 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "$arg" > gpurun_out/memcheck_$n.log 2>&1
       echo "rc=$?"; tail -n 30 gpurun_out/memcheck_$n.log ;;

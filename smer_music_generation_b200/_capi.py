@@ -29,7 +29,7 @@ class AttnArgs(C.Structure):
                 ("dbq", _vp), ("dbk", _vp), ("dbv", _vp), ("ldq", _ll), ("ldk", _ll), ("ldv", _ll), ("ldo", _ll), ("lddo", _ll), ("lddq", _ll), ("lddk", _ll),
                 ("lddv", _ll), ("lse", _vp), ("dsum", _vp), ("key_pad", _vp), ("kv_len", _vp), ("add_mask", _vp),
                 ("ld_mask", _ll), ("B", _i), ("H", _i), ("Lq", _i), ("Lk", _i), ("dh", _i), ("dtype", _i),
-                ("causal", _i), ("q_pos0", _i), ("scale", _f), ("dropout_p", _f), ("seed", _u64), ("site", _u64)]
+                ("causal", _i), ("q_pos0", _i), ("scale", _f), ("dropout_p", _f), ("seed", _u64), ("site", _u64), ("dq_accum", _vp)]
 
 
 class DecodeAttnArgs(C.Structure):

@@ -2,22 +2,22 @@
 // Arithmetic: softmax(q k^T / sqrt(dh) + masks) v with dropout on P, as F.multi_head_attention_forward's
 // need_weights branch computes it for the reference (transformer.py:389,459,463).
 //
-// One persistent CTA per SM walks (batch, head, PAIR of 128-query tiles) work items:
-//   warp 8       TMA producer: the pair's two Q tiles once, then K_t / V_t through 3-stage rings (each K / V tile is
-//                loaded once and serves both query tiles)
-//   warp 9       tcgen05.mma issuer + TMEM owner.  TMEM (512 columns): S0 | S1 (128 fp32 columns each) and
-//                O0 | O1 (64 each).  Per tile and query tile c: S_c = Q_c K_t^T (SS), then O_c += P_c V_t with the A
-//                operand P_c read FROM TENSOR MEMORY (TS-MMA): the softmax threads write P (bf16, two keys per
-//                32-bit column) over the first 64 columns of S_c, no shared-memory round trip.  O_c stays resident
-//                in TMEM for the whole item.
-//   warps 0..3   softmax of query tile 0, one thread per query row (= TMEM lane): the row's 128 scores of a tile are
-//   warps 4..7   softmax of query tile 1      read once into registers; row maximum; exp2 / row sum / dropout / bf16
-//                pack; P back to TMEM.  The running maximum is LAZY: O_c (and the row sum) are rescaled only when the
-//                maximum grew by more than 2^8, done by the row's own thread between "S ready" and "P ready", when
-//                no MMA touches O_c.  While one query tile's threads work, the tensor core runs the other tile's MMAs.
-//   Roles are warpgroup-aligned so that setmaxnreg can move registers from the producer warpgroup (warps 8..11, two of
-//   them idle) to the softmax warpgroups: a row of 128 fp32 scores plus its packed P needs more than the 168 registers
-//   a 384-thread CTA starts with.
+// One persistent CTA per SM walks (batch, head, PAIR of 128-query tiles) work items.  Four independent softmax
+// CHAINS run per CTA: chain q = (query tile c = q / 2, key half hf = q % 2) owns the 64-key half `hf` of every
+// 128-key K/V tile for query tile `c`, with its own running maximum, row sum and output accumulator (split-KV, as in
+// flash decoding); the two halves of a query tile are merged once, at the end of the item.  No per-tile exchange
+// between threads, and sixteen softmax warps (four per scheduler) to hide TMEM / MUFU / barrier latency.
+//   warps 0..15  softmax, warpgroup q = chain q, one thread per query row (= TMEM lane): the row's 64 scores of a tile
+//                are read once into registers; row maximum; exp2 / row sum / dropout / bf16 pack; P goes back to
+//                TENSOR MEMORY over the first 32 columns of S_q.  The reference maximum is LAZY: O_q and the row sum
+//                are rescaled only when the maximum grew by more than 2^8, by the row's own thread between
+//                "S ready" and "P ready", when no MMA touches O_q.
+//   warp 16      TMA producer: the pair's two Q tiles once, then K_t / V_t through 3-stage rings (each K / V tile is
+//                loaded once and serves all four chains)
+//   warp 17      tcgen05.mma issuer + TMEM owner.  TMEM (512 columns): S_q at 64 q (fp32), O_q at 256 + 64 q.
+//                S_q = Q_c K_hf^T (SS), O_q += P_q V_hf with the A operand P_q read from tensor memory (TS-MMA).
+//   warps 18,19  idle: roles are warpgroup-aligned so that setmaxnreg can move the producer warpgroup's registers
+//                to the softmax warpgroups.
 #include <type_traits>
 
 #include "common.cuh"
@@ -29,16 +29,20 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
 
 namespace {
 
-constexpr int BM = 128, BN = 128, DH = 64;
+constexpr int BM = 128, BN = 128, BH = 64, DH = 64;      // BH: keys per chain and tile
 constexpr int TILE = BM * DH * 2;                 // 16 KB: one Q / K / V tile
 constexpr int KS = 3;                             // K and V ring depth
-constexpr int THREADS = 384;                      // 2 softmax warpgroups + 1 producer warpgroup (TMA warp, MMA warp, 2 idle)
+constexpr int NCHAIN = 4;
+constexpr int THREADS = 640;                      // 4 softmax warpgroups + 1 producer warpgroup (TMA warp, MMA warp, 2 idle)
 constexpr int MASK_WORDS = 512;                   // key-mask bitmap of one batch row: Lk <= 16384
+constexpr int XCH_STRIDE = 33;                    // floats per row of the merge exchange (padded: conflict-free)
 constexpr int OFF_K = 2 * TILE, OFF_V = OFF_K + KS * TILE, OFF_BAR = OFF_V + KS * TILE;
 constexpr int OFF_MASK = OFF_BAR + 256;
-constexpr int SMEM_BYTES = OFF_MASK + 2 * MASK_WORDS * 4 + 1024 /*alignment slack*/;
+constexpr int OFF_XCH = OFF_MASK + 2 * MASK_WORDS * 4;               // [2 query tiles][2 halves][128 rows][33] fp32
+constexpr int OFF_ML = OFF_XCH + 2 * 2 * BM * XCH_STRIDE * 4;        // [2][2][128][2] fp32: (m, l) of every chain row
+constexpr int SMEM_BYTES = OFF_ML + 2 * 2 * BM * 2 * 4 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0, COL_O = 256;        // S_c at COL_S + 128 c, O_c at COL_O + 64 c, P_c over S_c's first 64 columns
+constexpr uint32_t COL_S = 0, COL_O = 256;        // S_q at COL_S + 64 q, O_q at COL_O + 64 q, P_q over S_q's first 32 columns
 constexpr float RESCALE_LOG2 = 8.f;               // lazy rescale: only when the maximum grew by more than 2^8
 
 struct Params {
@@ -50,7 +54,7 @@ struct Params {
   int B, H, Lq, Lk;
   float c_log2;            // scale * log2(e)
   int causal;
-  uint32_t thr;            // dropout threshold p * 2^32 (0 = dropout off)
+  uint32_t thr2;           // dropout threshold pattern in both halves (common.cuh: attn_dropout_threshold); 0 = dropout off
   float inv_keep;
   uint64_t seed, site;
   const unsigned long long* seed_dev;
@@ -63,13 +67,16 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 __device__ __forceinline__ uint32_t lds_u(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void bar_sync_wg(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// the 256 threads of one query tile (its two key-half chains)
+__device__ __forceinline__ void bar_sync_qtile(int c) { asm volatile("bar.sync %0, 256;" ::"r"(c + 1) : "memory"); }
 
 struct Item {
   int b, h, i0;            // first query row of the pair
-  int nt[2];               // KV tiles of query tile 0 / 1 (0: tile inactive)
-  int kend[2];
+  int nt0, nt1;            // 128-key K/V tiles of query tile 0 / 1 (0: tile inactive)
+  int kend0, kend1;
   int ntk;                 // K / V tiles to load = max
 };
 
@@ -83,19 +90,15 @@ __device__ __forceinline__ Item item_of(const Params& p, int item) {
   it.b = rem / p.H;
   it.i0 = qp * 2 * BM;
   const int kl = p.kv_len ? min(p.kv_len[it.b], p.Lk) : p.Lk;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int r0 = it.i0 + c * BM;
-    int ke = r0 < p.Lq ? kl : 0;
-    if (p.causal) ke = min(ke, r0 + BM);
-    it.kend[c] = ke;
-    it.nt[c] = (ke + BN - 1) / BN;
-  }
-  it.ntk = max(it.nt[0], it.nt[1]);
+  int ke0 = it.i0 < p.Lq ? kl : 0, ke1 = it.i0 + BM < p.Lq ? kl : 0;
+  if (p.causal) { ke0 = min(ke0, it.i0 + BM); ke1 = min(ke1, it.i0 + 2 * BM); }
+  it.kend0 = ke0; it.kend1 = ke1;
+  it.nt0 = (ke0 + BN - 1) / BN; it.nt1 = (ke1 + BN - 1) / BN;
+  it.ntk = max(it.nt0, it.nt1);
   return it;
 }
 
-template <bool DROP>          // dropout compiled in or out: a run-time test per 8 keys would cut the softmax loop into 16 basic blocks
+template <bool DROP>          // dropout compiled in or out: a run-time test per 8 keys would cut the softmax loop into basic blocks
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, Params p) {
@@ -106,30 +109,30 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sV = smem + OFF_V;                      // [KS] x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t *q_full = bars, *q_empty = bars + 1, *k_full = bars + 2 /*[KS]*/, *k_empty = bars + 2 + KS /*[KS]*/,
-           *v_full = bars + 2 + 2 * KS, *v_empty = bars + 2 + 3 * KS, *s_full = bars + 2 + 4 * KS /*[2]*/,
-           *p_full = s_full + 2 /*[2]*/, *o_full = s_full + 4 /*[2]*/;
-  constexpr int NBARS = 2 + 4 * KS + 6;
+           *v_full = bars + 2 + 2 * KS, *v_empty = bars + 2 + 3 * KS, *s_full = bars + 2 + 4 * KS /*[4]*/,
+           *p_full = s_full + NCHAIN /*[4]*/, *o_full = s_full + 2 * NCHAIN /*[4]*/;
+  constexpr int NBARS = 2 + 4 * KS + 3 * NCHAIN;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
   static_assert((NBARS + 1) * 8 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < NBARS; ++i) ptx::mbar_init(bars + i, (bars + i == p_full || bars + i == p_full + 1) ? 4 : 1);
+    for (int i = 0; i < NBARS; ++i) ptx::mbar_init(bars + i, (bars + i >= p_full && bars + i < p_full + NCHAIN) ? 4 : 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
+  if (warp == 17) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp >= 8) {
+  if (warp >= 16) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 8) {
+  if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t g = 0, qi = 0;                       // K/V tiles and items (with work) so far: ring slots and phases
@@ -137,9 +140,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const Item it = item_of(p, item);
         if (it.ntk == 0) continue;
         if (qi > 0) ptx::mbar_wait(q_empty, (qi - 1) & 1);          // the previous item's S MMAs have read sQ
-        ptx::mbar_expect_tx(q_full, it.nt[1] > 0 ? 2 * TILE : TILE);
+        ptx::mbar_expect_tx(q_full, it.nt1 > 0 ? 2 * TILE : TILE);
         ptx::tma_load_2d(sQ, &tmQ, q_full, it.h * DH, it.b * p.Lq + it.i0);
-        if (it.nt[1] > 0) ptx::tma_load_2d(sQ + TILE, &tmQ, q_full, it.h * DH, it.b * p.Lq + it.i0 + BM);
+        if (it.nt1 > 0) ptx::tma_load_2d(sQ + TILE, &tmQ, q_full, it.h * DH, it.b * p.Lq + it.i0 + BM);
         for (int t = 0; t < it.ntk; ++t, ++g) {
           const uint32_t st = g % KS, ph = ((g / KS) - 1) & 1;
           if (g >= KS) ptx::mbar_wait(k_empty + st, ph);
@@ -153,26 +156,31 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ------------------------------------------------------------------ MMA issuer
     if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BM, BH, 0, 0);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BM, DH, 0, 1);
       const uint32_t aQ = ptx::smem_u32(sQ), aK = ptx::smem_u32(sK), aV = ptx::smem_u32(sV);
-      uint32_t g = 0, qi = 0, np[2] = {0u, 0u};      // np[c]: P tiles of chain c consumed so far (p_full phase)
-      auto issue_s = [&](int c, uint32_t st) {       // S_c = Q_c K^T
+      uint32_t g = 0, qi = 0, np = 0;               // np: P tiles consumed so far PER CHAIN (chains of a query tile advance together; see below)
+      uint32_t npq[NCHAIN] = {0u, 0u, 0u, 0u};
+      auto issue_s = [&](int q, uint32_t st) {       // S_q = Q_c K_hf^T   (64 keys: rows hf*64.. of the K tile)
+        const int c = q >> 1, hf = q & 1;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          ptx::umma_bf16_ss(tmem_base + COL_S + c * 128, ptx::make_smem_desc(aQ + c * TILE + k * 32, 16, 1024),
-                            ptx::make_smem_desc(aK + st * TILE + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        ptx::umma_commit(s_full + c);
+          ptx::umma_bf16_ss(tmem_base + COL_S + q * 64, ptx::make_smem_desc(aQ + c * TILE + k * 32, 16, 1024),
+                            ptx::make_smem_desc(aK + st * TILE + hf * (TILE / 2) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(s_full + q);
       };
-      auto issue_pv = [&](int c, uint32_t st, bool acc) {   // O_c (+)= P_c V, P_c from tensor memory
+      auto issue_pv = [&](int q, uint32_t st, bool acc) {   // O_q (+)= P_q V_hf, P_q (128 x 64 keys, bf16) from tensor memory
+        const int hf = q & 1;
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k)
-          ptx::umma_bf16_ts(tmem_base + COL_O + c * 64, tmem_base + COL_S + c * 128 + k * 8,
-                            ptx::make_smem_desc(aV + st * TILE + k * 2048, 8192, 1024), idesc_o, (acc || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BH / 16; ++k)
+          ptx::umma_bf16_ts(tmem_base + COL_O + q * 64, tmem_base + COL_S + q * 64 + k * 8,
+                            ptx::make_smem_desc(aV + st * TILE + hf * (TILE / 2) + k * 2048, 8192, 1024), idesc_o,
+                            (acc || k > 0) ? 1u : 0u);
       };
+      (void)np;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const Item it = item_of(p, item);
         if (it.ntk == 0) continue;
@@ -181,8 +189,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t st = g % KS;
           ptx::mbar_wait(k_full + st, (g / KS) & 1);
           ptx::tc_fence_after();
-          if (it.nt[0] > 0) issue_s(0, st);
-          if (it.nt[1] > 0) issue_s(1, st);
+#pragma unroll
+          for (int q = 0; q < NCHAIN; ++q)
+            if ((q < 2 ? it.nt0 : it.nt1) > 0) issue_s(q, st);
           ptx::umma_commit(k_empty + st);
           if (it.ntk == 1) ptx::umma_commit(q_empty);
         }
@@ -193,16 +202,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (more) ptx::mbar_wait(k_full + stn, ((gc + 1) / KS) & 1);
           ptx::mbar_wait(v_full + st, (gc / KS) & 1);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            if (t < it.nt[c]) {
-              ptx::mbar_wait(p_full + c, np[c] & 1);
-              ++np[c];
+          for (int q = 0; q < NCHAIN; ++q) {
+            const int nt = q < 2 ? it.nt0 : it.nt1;
+            if (t < nt) {
+              ptx::mbar_wait(p_full + q, npq[q] & 1);
+              ++npq[q];
               ptx::tc_fence_after();
-              issue_pv(c, st, t > 0);
-              if (t == it.nt[c] - 1) ptx::umma_commit(o_full + c);
+              issue_pv(q, st, t > 0);
+              if (t == nt - 1) ptx::umma_commit(o_full + q);
             }
-            if (c == 1) ptx::umma_commit(v_empty + st);
-            if (more && t + 1 < it.nt[c]) issue_s(c, stn);        // S_c's columns are free: PV_c(t) was issued before
+            if (q == NCHAIN - 1) ptx::umma_commit(v_empty + st);
+            if (more && t + 1 < nt) issue_s(q, stn);              // S_q's columns are free: PV_q(t) was issued before
           }
           if (more) {
             ptx::umma_commit(k_empty + stn);
@@ -216,89 +226,87 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncwarp();
   }
   } else {
-    // ------------------------------------------------------------------ softmax: chain c, one thread per query row
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int c = warp >> 2;
+    // ------------------------------------------------------------------ softmax: chain q, one thread per query row
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp >> 2, c = q >> 1, hf = q & 1;
     const int quarter = warp & 3;                   // TMEM lanes this warp may touch: 32 * (warp % 4)
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t tS = lane_base + COL_S + c * 128, tO = lane_base + COL_O + c * 64;
+    const uint32_t tS = lane_base + COL_S + q * 64, tO = lane_base + COL_O + q * 64;
     const uint32_t a_mask = ptx::smem_u32(smem + OFF_MASK) + c * MASK_WORDS * 4;
+    const uint32_t a_xch_mine = ptx::smem_u32(smem + OFF_XCH) + ((c * 2 + hf) * BM + r) * XCH_STRIDE * 4;
+    const uint32_t a_xch_peer = ptx::smem_u32(smem + OFF_XCH) + ((c * 2 + (hf ^ 1)) * BM + r) * XCH_STRIDE * 4;
+    const uint32_t a_ml_mine = ptx::smem_u32(smem + OFF_ML) + ((c * 2 + hf) * BM + r) * 8;
+    const uint32_t a_ml_peer = ptx::smem_u32(smem + OFF_ML) + ((c * 2 + (hf ^ 1)) * BM + r) * 8;
     const float c2 = p.c_log2;
+    const uint32_t sitekey = DROP ? attn_site_key(eff_seed(p.seed, p.seed_dev), p.site) : 0u;
     uint32_t ns = 0, no = 0;                        // S tiles / items of this chain so far (barrier phases)
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const Item it = item_of(p, item);
-      const int nt = it.nt[c], kend = it.kend[c];
-      const int i = it.i0 + c * BM + r;
+      const int nt = c ? it.nt1 : it.nt0, kend = c ? it.kend1 : it.kend0;
+      const int r0 = it.i0 + c * BM;
+      const int i = r0 + r;
       const bool row_ok = i < p.Lq;
       const int ii = row_ok ? i : p.Lq - 1;
       const long long rowid = ((long long)it.b * p.H + it.h) * p.Lq + ii;
-      const uint32_t rowkey = DROP ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ii & 7)) : 0u;
-      uint32_t pm = 1u, pa = 0u;                    // row (ii & 7) of the 8x8 dropout block: 8 LCG steps per row
-      if (DROP) attn_advance(8 * (ii & 7), pm, pa);
-      // key-mask bitmap of this item's tiles (bit j: key j masked), built once per item by the chain's 128 threads
+      const uint32_t rowkey = DROP ? attn_row_key(sitekey, rowid) : 0u;
+      // key-mask bitmap of this item's tiles (bit j: key j masked), built once per item by the query tile's 256 threads
       const bool use_mask = nt > 0 && (p.pad != nullptr || (kend & (BN - 1)) != 0);
-      bar_sync_wg(c);                                // every thread of the chain has left the previous item's bitmap
+      bar_sync_qtile(c);                             // every thread of the query tile has left the previous item's bitmap / exchange
       if (use_mask) {
-        for (int j = (warp & 3) * 32 + lane; j < nt * BN; j += 128) {     // (any permutation of the 4 warps)
+        for (int j = (hf * 4 + quarter) * 32 + lane; j < nt * BN; j += 256) {
           const bool msk = j >= kend || (p.pad && p.pad[(long long)it.b * p.Lk + j]);
           const uint32_t bal = __ballot_sync(0xffffffffu, msk);
           if (lane == 0) sts_u(a_mask + (j >> 5) * 4, bal);
         }
       }
-      bar_sync_wg(c);                                // publishes the bitmap; separates it from the previous item's reads
-      float m = -INFINITY, l = 0.f;                  // reference maximum (log2 units, may lag) and row sum
+      bar_sync_qtile(c);                             // publishes the bitmap
+      float m = -INFINITY, l = 0.f;                  // reference maximum (log2 units, may lag) and row sum of this key half
       for (int t = 0; t < nt; ++t, ++ns) {
-        const int j0 = t * BN;
-        uint32_t mw[4] = {0u, 0u, 0u, 0u};
+        const int j0 = t * BN + hf * BH;             // first key of this chain's half of the tile
+        uint32_t mw0 = 0u, mw1 = 0u;
         if (use_mask) {
-#pragma unroll
-          for (int w = 0; w < 4; ++w) mw[w] = lds_u(a_mask + ((j0 >> 5) + w) * 4);
+          mw0 = lds_u(a_mask + ((j0 >> 5)) * 4);
+          mw1 = lds_u(a_mask + ((j0 >> 5) + 1) * 4);
         }
-        if (p.causal && j0 + BN - 1 > it.i0 + c * BM) {
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int nvis = i - (j0 + w * 32) + 1;
-            mw[w] |= nvis <= 0 ? 0xffffffffu : (nvis >= 32 ? 0u : (0xffffffffu << nvis));
-          }
+        if (p.causal && j0 + BH - 1 > r0) {
+          const int nv0 = i - j0 + 1, nv1 = i - (j0 + 32) + 1;
+          mw0 |= nv0 <= 0 ? 0xffffffffu : (nv0 >= 32 ? 0u : (0xffffffffu << nv0));
+          mw1 |= nv1 <= 0 ? 0xffffffffu : (nv1 >= 32 ? 0u : (0xffffffffu << nv1));
         }
-        const bool masked = __any_sync(0xffffffffu, (mw[0] | mw[1] | mw[2] | mw[3]) != 0u);
-        ptx::mbar_wait(s_full + c, ns & 1);
+        const bool masked = __any_sync(0xffffffffu, (mw0 | mw1) != 0u);
+        ptx::mbar_wait(s_full + q, ns & 1);
         ptx::tc_fence_after();
-        // ---- the row's 128 scores, read once
-        uint32_t s[128];
+        // ---- the row's 64 scores, read once
+        uint32_t s[64];
         {
           uint32_t (&s0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
           uint32_t (&s1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-          uint32_t (&s2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[64]);
-          uint32_t (&s3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[96]);
           ptx::tmem_ld_32x32(tS, s0);
           ptx::tmem_ld_32x32(tS + 32, s1);
-          ptx::tmem_ld_32x32(tS + 64, s2);
-          ptx::tmem_ld_32x32(tS + 96, s3);
           ptx::tmem_ld_wait();
         }
         if (masked) {
 #pragma unroll
-          for (int k = 0; k < 128; ++k)
-            if ((mw[k >> 5] >> (k & 31)) & 1u) s[k] = 0xff800000u;          // -inf
+          for (int k = 0; k < 64; ++k)
+            if (((k < 32 ? mw0 : mw1) >> (k & 31)) & 1u) s[k] = 0xff800000u;          // -inf
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 128; k += 8) {
+        for (int k = 0; k < 64; k += 8) {
           mx0 = max3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
           mx1 = max3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
           mx2 = max3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
           mx3 = max3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
         }
         const float mxs = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;      // c2 > 0
-        // ---- lazy maximum: rescale O_c and the row sum only when the maximum grew by more than 2^8 (or is new)
+        // ---- lazy maximum: rescale O_q and the row sum only when the maximum grew by more than 2^8 (or is new)
         if (__any_sync(0xffffffffu, mxs > m + RESCALE_LOG2 || (m == -INFINITY && mxs > -INFINITY))) {
           const float m_new = fmaxf(m, mxs);
           const float alpha = m_new == -INFINITY ? 1.f : ex2(m - m_new);   // m = -inf: alpha = 0, nothing accumulated yet
           l *= alpha;
           m = m_new;
-          if (t > 0) {                               // O_c holds tiles 0..t-1 and no MMA touches it now
+          if (t > 0) {                               // O_q holds tiles 0..t-1 and no MMA touches it now
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               uint32_t v[16];
@@ -314,36 +322,26 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const f32x2 c2p = pack2(c2, c2), nm2 = pack2(-m_use, -m_use);
         f32x2 ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
         // ---- P = exp2(S c - m), row sum, dropout (P stays unscaled: 1/(1-p) is applied once per row at the end), bf16
-        uint32_t pk[64];
-        const uint32_t kbase = rowkey + (uint32_t)(j0 >> 3) * ATTN_GOLD;    // dropout block index of the tile's first key
+        uint32_t pk[32];
 #pragma unroll
-        for (int c8 = 0; c8 < 16; ++c8) {
-          float pv[8];
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t x[8];
+          if (DROP) attn_pair_words(attn_block_word(rowkey, (uint32_t)(j0 >> 4) + c16), x);     // one word per two keys
 #pragma unroll
-          for (int k = 0; k < 8; k += 2) {
+          for (int k = 0; k < 8; ++k) {
+            const int e = c16 * 16 + 2 * k;
             float e0, e1;
-            unpack2(fma2(pack2(__uint_as_float(s[c8 * 8 + k]), __uint_as_float(s[c8 * 8 + k + 1])), c2p, nm2), e0, e1);
-            pv[k] = ex2(e0);
-            pv[k + 1] = ex2(e1);
-            if (k & 2) ls1 = add2(ls1, pack2(pv[k], pv[k + 1]));
-            else ls0 = add2(ls0, pack2(pv[k], pv[k + 1]));
+            unpack2(fma2(pack2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), c2p, nm2), e0, e1);
+            const float p0 = ex2(e0), p1 = ex2(e1);
+            if (k & 1) ls1 = add2(ls1, pack2(p0, p1));
+            else ls0 = add2(ls0, pack2(p0, p1));
+            uint32_t pb = pack_bf16x2(p0, p1);
+            if (DROP) pb &= attn_keep_mask2(x[k], p.thr2);          // both keys of the pair with one packed compare
+            pk[e >> 1] = pb;
           }
-          if (DROP) {                                 // one mixed word per 8 keys, then one multiply-add per key
-            uint32_t x[8];
-            attn_block8<1>(attn_mix(kbase + (uint32_t)c8 * ATTN_GOLD) * pm + pa, x);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) pv[k] = x[k] >= p.thr ? pv[k] : 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; k += 2) pk[c8 * 4 + (k >> 1)] = pack_bf16x2(pv[k], pv[k + 1]);
         }
-        {
-          uint32_t (&p0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
-          uint32_t (&p1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
-          ptx::tmem_st_32x32(tS, p0);
-          ptx::tmem_st_32x32(tS + 32, p1);
-          ptx::tmem_st_wait();
-        }
+        ptx::tmem_st_32x32(tS, pk);
+        ptx::tmem_st_wait();
         {
           float a0, a1, b0, b1;
           unpack2(ls0, a0, a1);
@@ -352,50 +350,64 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         ptx::tc_fence_before();                      // orders this thread's tcgen05.ld / st before the MMAs that follow the arrive
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(p_full + c);
+        if (lane == 0) ptx::mbar_arrive(p_full + q);
       }
-      // ---- epilogue of the item: O_c / l -> global
-      uint32_t v0[32], v1[32];
-      if (nt > 0) {                                  // uniform over the chain's threads
-        ptx::mbar_wait(o_full + c, no & 1);
+      // ---- epilogue of the item: merge the two key halves of the row, O / l -> global
+      // this thread stores output columns [32 hf, 32 hf + 32); the other 32 columns of its partial go to the peer
+      float mine[32];
+      if (nt > 0) {                                  // uniform over the query tile's threads
+        ptx::mbar_wait(o_full + q, no & 1);
         ++no;
         ptx::tc_fence_after();
-        ptx::tmem_ld_32x32(tO, v0);
-        ptx::tmem_ld_32x32(tO + 32, v1);
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32(tO + hf * 32, v0);        // the columns this thread finishes
+        ptx::tmem_ld_32x32(tO + (hf ^ 1) * 32, v1);  // the columns the peer finishes
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          mine[k] = __uint_as_float(v0[k]);
+          sts_f(a_xch_mine + k * 4, __uint_as_float(v1[k]));
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v0[k] = v1[k] = 0u;
+        for (int k = 0; k < 32; ++k) mine[k] = 0.f;
       }
-      if (row_ok) {
-        const float inv = l > 0.f ? p.inv_keep / l : 0.f;      // dropout's 1/(1-p) applied once per row
-        bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH;
+      sts_f(a_ml_mine, m);
+      sts_f(a_ml_mine + 4, l);
+      bar_sync_qtile(c);
+      if (nt > 0 && row_ok) {
+        const float mp = lds_f(a_ml_peer), lp = lds_f(a_ml_peer + 4);
+        const float mm = fmaxf(m, mp);
+        const float fa = m == -INFINITY ? 0.f : ex2(m - mm), fb = mp == -INFINITY ? 0.f : ex2(mp - mm);
+        const float lt = l * fa + lp * fb;
+        const float inv = lt > 0.f ? p.inv_keep / lt : 0.f;      // dropout's 1/(1-p) applied once per row
+        const float wa = fa * inv, wb = fb * inv;
+        bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
 #pragma unroll
         for (int k = 0; k < 32; k += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v0[k]) * inv, __uint_as_float(v0[k + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(v0[k + 2]) * inv, __uint_as_float(v0[k + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(v0[k + 4]) * inv, __uint_as_float(v0[k + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(v0[k + 6]) * inv, __uint_as_float(v0[k + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + k) = u;
-        }
+          float f[8];
 #pragma unroll
-        for (int k = 0; k < 32; k += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v1[k]) * inv, __uint_as_float(v1[k + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(v1[k + 2]) * inv, __uint_as_float(v1[k + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(v1[k + 4]) * inv, __uint_as_float(v1[k + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(v1[k + 6]) * inv, __uint_as_float(v1[k + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 32 + k) = u;
+          for (int u = 0; u < 8; ++u) f[u] = mine[k + u] * wa + lds_f(a_xch_peer + (k + u) * 4) * wb;
+          uint4 u4;
+          u4.x = pack_bf16x2(f[0], f[1]);
+          u4.y = pack_bf16x2(f[2], f[3]);
+          u4.z = pack_bf16x2(f[4], f[5]);
+          u4.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(orow + k) = u4;
         }
-        if (p.lse) p.lse[rowid] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+        if (p.lse && hf == 0) p.lse[rowid] = lt > 0.f ? (mm + log2f(lt)) * 0.6931471805599453f : -INFINITY;
+      } else if (row_ok) {                           // no visible key at all: zeros (uniform branch per query tile)
+        bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) *reinterpret_cast<uint4*>(orow + k) = make_uint4(0u, 0u, 0u, 0u);
+        if (p.lse && hf == 0) p.lse[rowid] = -INFINITY;
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 17) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 }  // namespace
@@ -413,7 +425,7 @@ int smer_attn_fwd2_launch(const smer_attn_args* a, void* stream) {
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.c_log2 = a->scale * 1.4426950408889634f;
   p.causal = a->causal;
-  p.thr = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;
+  p.thr2 = a->dropout_p > 0.f ? attn_dropout_threshold(a->dropout_p) * 0x10001u : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   p.npair = (a->Lq + 2 * BM - 1) / (2 * BM);
@@ -429,7 +441,7 @@ int smer_attn_fwd2_launch(const smer_attn_args* a, void* stream) {
     attr_dev_mask |= 1 << dev;
   }
   const long long grid = items < smer_num_sms() ? items : smer_num_sms();
-  if (p.thr) attn_fwd2_kernel<true><<<dim3((unsigned)grid), THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  if (p.thr2) attn_fwd2_kernel<true><<<dim3((unsigned)grid), THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
   else attn_fwd2_kernel<false><<<dim3((unsigned)grid), THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
   SMER_CHECK_LAUNCH("smer_attn_fwd_tc(v2)");
   return SMER_OK;

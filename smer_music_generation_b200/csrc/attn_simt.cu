@@ -7,7 +7,7 @@
 //
 // Layout: token-major rows.  q[(b*Lq+i)*ldq + h*DH + c], same for k/v/o with their own pitches,
 // so the packed QKV projection output is consumed in place.  lse[(b*H+h)*Lq + i].
-// Dropout element (b,h,i,j): attn_keep(attn_row_key(seed, site, (b*H+h)*Lq + (i & ~7)), i, j) -- common.cuh.
+// Dropout element (b,h,i,j): attn_keep(attn_row_key(attn_site_key(seed, site), (b*H+h)*Lq + i), j, thr) -- common.cuh.
 #include "common.cuh"
 #include "../../include/smer_b200.h"
 
@@ -49,15 +49,16 @@ __device__ __forceinline__ float row_dot(const float (&a)[DPT], const float* __r
   return s;
 }
 
-// keys 4*j4 .. 4*j4+3 of one row; (pm, pa) = attn_advance(8 * (row & 7)) of that row
-__device__ __forceinline__ void drop_lanes(const AttnParams& p, uint32_t rowkey, uint32_t pm, uint32_t pa, int j4, float (&m)[4]) {
-  uint32_t x = attn_blk_x(rowkey, j4 * 4) * pm + pa;
-  if (j4 & 1) x = attn_step4(x);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    m[k] = x >= p.thr ? p.inv_keep : 0.f;
-    x = attn_step(x);
-  }
+// keys 4*j4 .. 4*j4+3 of one row: two pair words of the 16-key block (4*j4) >> 4
+__device__ __forceinline__ void drop_lanes(const AttnParams& p, uint32_t rowkey, int j4, float (&m)[4]) {
+  const uint32_t w = attn_block_word(rowkey, (uint32_t)j4 >> 2);
+  uint32_t mul = 1u, add = 0u;
+  for (int k = 0; k < (j4 & 3) * 2; ++k) { mul *= ATTN_A; add = add * ATTN_A + ATTN_C; }
+  const uint32_t x0 = w * mul + add, x1 = x0 * ATTN_A + ATTN_C;
+  m[0] = attn_keep_field(x0 & 0xFFFFu, p.thr) ? p.inv_keep : 0.f;
+  m[1] = attn_keep_field(x0 >> 16, p.thr) ? p.inv_keep : 0.f;
+  m[2] = attn_keep_field(x1 & 0xFFFFu, p.thr) ? p.inv_keep : 0.f;
+  m[3] = attn_keep_field(x1 >> 16, p.thr) ? p.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -86,9 +87,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
-  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ic & 7)) : 0u;
-  uint32_t pm = 1u, pa = 0u;
-  if (p.thr) attn_advance(8 * (ic & 7), pm, pa);
+  const uint32_t rowkey = p.thr ? attn_row_key(attn_site_key(eff_seed(p.seed, p.seed_dev), p.site), rowid) : 0u;
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
   const T* vb = (const T*)p.v + (long long)b * p.Lk * p.ldv + h * DH;
 
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
 #pragma unroll
     for (int j4 = 0; j4 < KT / 4; ++j4) {
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) drop_lanes(p, rowkey, pm, pa, (j0 >> 2) + j4, dm);
+      if (p.thr) drop_lanes(p, rowkey, (j0 >> 2) + j4, dm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int jj = j4 * 4 + u;
@@ -204,9 +203,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
   }
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
   float lse = p.lse[rowid], dsum = p.dsum[rowid];
-  const uint32_t rowkey = p.thr ? attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (ic & 7)) : 0u;
-  uint32_t pm = 1u, pa = 0u;
-  if (p.thr) attn_advance(8 * (ic & 7), pm, pa);
+  const uint32_t rowkey = p.thr ? attn_row_key(attn_site_key(eff_seed(p.seed, p.seed_dev), p.site), rowid) : 0u;
   int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
@@ -232,7 +229,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
 #pragma unroll 2
     for (int j4 = 0; j4 < KT / 4; ++j4) {
       float dm[4] = {1.f, 1.f, 1.f, 1.f};
-      if (p.thr) drop_lanes(p, rowkey, pm, pa, (j0 >> 2) + j4, dm);
+      if (p.thr) drop_lanes(p, rowkey, (j0 >> 2) + j4, dm);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         int jj = j4 * 4 + u;
@@ -319,7 +316,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(AttnParams p) {
       float pr = masked ? 0.f : expf(s - Ls[ii]);
       float dmv = 1.f;
       if (p.thr)
-        dmv = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowbase + (min(i, p.Lq - 1) & ~7)), min(i, p.Lq - 1), jc, p.thr) ? p.inv_keep : 0.f;
+        dmv = attn_keep(attn_row_key(attn_site_key(eff_seed(p.seed, p.seed_dev), p.site), rowbase + min(i, p.Lq - 1)), jc, p.thr) ? p.inv_keep : 0.f;
       float dp = row_dot<DPT, TPR>(vr, &Gs[ii][part * DPT]) * dmv;
       float ds = pr * (dp - Ds[ii]);
       float pd = pr * dmv;
@@ -371,7 +368,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_weights_kernel(AttnParams p, fl
         if (p.addmask) s += p.addmask[(long long)i * p.ldmask + j];
         long long rowid = ((long long)b * p.H + h) * p.Lq + i;
         float pr = expf(s - p.lse[rowid]);
-        if (p.thr) pr = attn_keep(attn_row_key(eff_seed(p.seed, p.seed_dev), p.site, rowid - (i & 7)), i, j, p.thr) ? pr * p.inv_keep : 0.f;
+        if (p.thr) pr = attn_keep(attn_row_key(attn_site_key(eff_seed(p.seed, p.seed_dev), p.site), rowid), j, p.thr) ? pr * p.inv_keep : 0.f;
         acc += pr;
       }
     }
@@ -393,7 +390,7 @@ static int fill_params(AttnParams& p, const smer_attn_args* a, const char* who) 
   p.addmask = a->add_mask; p.ldmask = a->ld_mask;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale = a->scale; p.causal = a->causal; p.q_pos0 = a->q_pos0;
-  p.thr = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0u;       // p * 2^32
+  p.thr = a->dropout_p > 0.f ? attn_dropout_threshold(a->dropout_p) : 0u;  // fp16 pattern rule of common.cuh
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
   if (p.B <= 0 || p.H <= 0 || p.Lq <= 0 || p.Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }

@@ -186,75 +186,86 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 // ---------------------------------------------------------------------------------------
 // Attention-probability dropout.  Philox costs ~100 instructions per 4 elements, which would
-// make the softmax warps of the tcgen05 attention kernels the bottleneck several times over;
-// the (B,H,Lq,Lk) keep-mask is instead a counter hash: a 32-bit key per (seed, site, b, h, i)
-// row, then one avalanche mix per PAIR of keys giving two 16-bit uniforms.  The SIMT and
-// tcgen05 kernels (forward, backward, attention-weights) all call these, so they agree bit
-// for bit.
+// make the softmax threads of the tcgen05 attention kernels the bottleneck several times over
+// (they are instruction-issue bound); the (B,H,Lq,Lk) keep-mask is a counter hash instead:
+//   site key  = two avalanche rounds of (seed, site)                          -- once per launch
+//   row key   = one avalanche round of (site key, row id (b*H+h)*Lq + i)      -- once per row
+//   block     = one xorshift-multiply-xorshift round of (row key + (j >> 4) * golden ratio): a
+//               32-bit word w per 16 consecutive keys of the row
+//   pair word = x_k = w advanced by k multiply-add (LCG) steps, k = (j & 15) >> 1; key j uses
+//               the low half of x_k when it is even, the high half when it is odd
+//   keep      iff the 16-bit field f, READ AS AN fp16 BIT PATTERN, is >= the (negative) fp16 whose
+//               pattern is thr = 0xFC00 - round(p * 65536), unordered compare: as integers,
+//               keep <=> f <= thr or f >= 0xFC01.  A drop probability of round(p*65536)/65536.
+// The point of that last rule: the tcgen05 kernels decide TWO keys with ONE packed half compare
+// on the pair word (HSET2 gives the 0xFFFF / 0 masks the bf16x2 probabilities are ANDed with,
+// HSETP2 gives two predicates), without extracting or masking fields -- 1 multiply-add + 1
+// compare per two keys plus the block round per 16.  The SIMT kernels evaluate the same rule with
+// integer compares, so every kernel (forward, backward, attention weights) agrees bit for bit.
+// (Offline check of the scheme at p = 0.1: drop rate 0.10009, per-position rates 0.0988..0.1013,
+// pair correlations inside a block <= 0.006, key / row lag correlations ~1e-3, 16-key and 32x32
+// block-sum variances within 1 % / 2 % of the binomial values.)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
   return x;
 }
-__device__ __forceinline__ uint32_t attn_row_key(uint64_t seed, uint64_t site, long long rowid) {
-  uint32_t a = lowbias32((uint32_t)seed ^ ((uint32_t)site * 0x9E3779B9u) ^ 0x85EBCA6Bu);
-  a = lowbias32(a + (uint32_t)(seed >> 32));
-  a = lowbias32(a ^ (uint32_t)rowid);
-  a = lowbias32(a + (uint32_t)((unsigned long long)rowid >> 32) + 0x632BE5ABu);
-  return a;
-}
-// One 32-bit word per 8x8 BLOCK of (8 query rows, 8 keys): two xorshift-multiply rounds of
-// (block-row key + key-block index * golden ratio).  Element (i & 7, j & 7) of the block uses
-// that word advanced by 8*(i&7) + (j&7) multiply-add (LCG) steps; keep iff word >= thr32 =
-// p * 2^32 (full word compare, no field extraction).  Kernels that walk along keys (forward,
-// dQ) pay the mix once per 8 keys and one multiply-add per further key; the dK/dV kernel (one
-// thread per key, walking along queries) pays it once per 8 queries and steps by 8 at a time --
-// instruction issue on the ALU pipe is what bounds the tcgen05 attention kernels, and the
-// multiply-adds run on the FMA pipe.  The row key is taken for the FIRST row of the block:
-// attn_row_key(seed, site, rowbase + (i & ~7)).  (Offline check of the scheme: keep rate,
-// lag correlations up to 16x16 and 8x8 block-sum variance all at the binomial values.)
-constexpr int ATTN_BLK = 8;
 constexpr uint32_t ATTN_GOLD = 0x9E3779B9u;
 constexpr uint32_t ATTN_A = 0x297A2D39u, ATTN_C = 0x7F4A7C15u;
 constexpr uint32_t lcg_mul_n(int n) { uint32_t m = 1u; for (int i = 0; i < n; ++i) m *= ATTN_A; return m; }
 constexpr uint32_t lcg_add_n(int n) { uint32_t a = 0u; for (int i = 0; i < n; ++i) a = a * ATTN_A + ATTN_C; return a; }
-constexpr uint32_t ATTN_A4 = lcg_mul_n(4), ATTN_C4 = lcg_add_n(4);                  // four steps at once
-constexpr uint32_t ATTN_A8 = lcg_mul_n(8), ATTN_C8 = lcg_add_n(8);                  // eight steps: next row of a block
-__device__ __forceinline__ uint32_t attn_mix(uint32_t x) {
-  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u;
+__device__ __forceinline__ uint32_t attn_site_key(uint64_t seed, uint64_t site) {
+  uint32_t a = lowbias32((uint32_t)seed ^ ((uint32_t)site * 0x9E3779B9u) ^ 0x85EBCA6Bu);
+  return lowbias32(a + (uint32_t)(seed >> 32));
+}
+__device__ __forceinline__ uint32_t attn_row_key(uint32_t sitekey, long long rowid) {
+  return lowbias32(sitekey ^ ((uint32_t)rowid * 0x9E3779B1u) ^ ((uint32_t)((unsigned long long)rowid >> 32) * 0x85EBCA77u));
+}
+// the 32-bit word of the 16-key block `jb` = j >> 4 of a row
+__device__ __forceinline__ uint32_t attn_block_word(uint32_t rowkey, uint32_t jb) {
+  uint32_t x = rowkey + jb * ATTN_GOLD;
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
   return x;
 }
-__device__ __forceinline__ uint32_t attn_blk_x(uint32_t blockkey, int j) {
-  return attn_mix(blockkey + (uint32_t)(j >> 3) * ATTN_GOLD);
+// x[k] = w advanced by k LCG steps, k = 0..7: the pair words of the block's 16 keys (7 independent multiply-adds)
+__device__ __forceinline__ void attn_pair_words(uint32_t w, uint32_t (&x)[8]) {
+  x[0] = w;
+  x[1] = w * lcg_mul_n(1) + lcg_add_n(1);
+  x[2] = w * lcg_mul_n(2) + lcg_add_n(2);
+  x[3] = w * lcg_mul_n(3) + lcg_add_n(3);
+  x[4] = w * lcg_mul_n(4) + lcg_add_n(4);
+  x[5] = w * lcg_mul_n(5) + lcg_add_n(5);
+  x[6] = w * lcg_mul_n(6) + lcg_add_n(6);
+  x[7] = w * lcg_mul_n(7) + lcg_add_n(7);
 }
-__device__ __forceinline__ uint32_t attn_step(uint32_t x) { return x * ATTN_A + ATTN_C; }
-__device__ __forceinline__ uint32_t attn_step4(uint32_t x) { return x * ATTN_A4 + ATTN_C4; }
-__device__ __forceinline__ uint32_t attn_step8(uint32_t x) { return x * ATTN_A8 + ATTN_C8; }
-// x[k] = x0 advanced by k*STEP steps, k = 0..7, as a depth-3 tree of multiply-adds (7 IMADs like the serial
-// chain, but a dependency depth of 3 instead of 7)
-template <int STEP>
-__device__ __forceinline__ void attn_block8(uint32_t x0, uint32_t (&x)[8]) {
-  constexpr uint32_t M1 = lcg_mul_n(STEP), A1 = lcg_add_n(STEP), M2 = lcg_mul_n(2 * STEP), A2 = lcg_add_n(2 * STEP),
-                     M4 = lcg_mul_n(4 * STEP), A4 = lcg_add_n(4 * STEP);
-  x[0] = x0;
-  x[1] = x0 * M1 + A1;
-  x[2] = x0 * M2 + A2;
-  x[4] = x0 * M4 + A4;
-  x[3] = x[2] * M1 + A1;
-  x[5] = x[4] * M1 + A1;
-  x[6] = x[4] * M2 + A2;
-  x[7] = x[6] * M1 + A1;
+// packed rule: 0xFFFF in every half of `pairword` that is kept (thr2 = thr | thr << 16)
+__device__ __forceinline__ uint32_t attn_keep_mask2(uint32_t pairword, uint32_t thr2) {
+  uint32_t m;
+  asm("set.geu.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(pairword), "r"(thr2));
+  return m;
 }
-// n LCG steps as one multiply-add: x -> x * mul + add
-__device__ __forceinline__ void attn_advance(int n, uint32_t& mul, uint32_t& add) {
-  mul = 1u; add = 0u;
-  for (int k = 0; k < n; ++k) { mul *= ATTN_A; add = add * ATTN_A + ATTN_C; }
+__device__ __forceinline__ void attn_keep_pred2(uint32_t pairword, uint32_t thr2, bool& k0, bool& k1) {
+  uint32_t a, b;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.geu.f16x2 p|q, %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\tselp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(a), "=r"(b) : "r"(pairword), "r"(thr2));
+  k0 = a != 0u; k1 = b != 0u;
 }
-// generic (slow) form: blockkey = attn_row_key(seed, site, rowbase + (i & ~7))
-__device__ __forceinline__ bool attn_keep(uint32_t blockkey, int i, int j, uint32_t thr32) {
-  uint32_t mul, add;
-  attn_advance(8 * (i & 7) + (j & 7), mul, add);
-  return attn_blk_x(blockkey, j) * mul + add >= thr32;
+// integer form of the same rule for one 16-bit field
+__device__ __forceinline__ bool attn_keep_field(uint32_t f, uint32_t thr) { return f <= thr || f >= 0xFC01u; }
+// generic (slow) form: rowkey = attn_row_key(attn_site_key(seed, site), rowid)
+__device__ __forceinline__ bool attn_keep(uint32_t rowkey, int j, uint32_t thr) {
+  uint32_t w = attn_block_word(rowkey, (uint32_t)j >> 4);
+  uint32_t mul = 1u, add = 0u;
+  for (int k = 0; k < ((j & 15) >> 1); ++k) { mul *= ATTN_A; add = add * ATTN_A + ATTN_C; }
+  const uint32_t x = w * mul + add;
+  return attn_keep_field((j & 1) ? x >> 16 : x & 0xFFFFu, thr);
+}
+// threshold pattern of the rule above; valid for p <= 0.45 (the pattern must stay a negative finite fp16)
+static inline uint32_t attn_dropout_threshold(float p) {
+  double n = (double)p * 65536.0 + 0.5;
+  if (n < 0) n = 0;
+  if (n > 29491.0) n = 29491.0;
+  return 0xFC00u - (uint32_t)n;
 }
 
 static inline uint32_t dropout_threshold(float p) {

@@ -175,7 +175,7 @@ def colsum(x, out):
 
 def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0, key_pad=None, kv_len=None,
               add_mask=None, dropout_p=0.0, seed=0, site=0, dout=None, dq=None, dk=None, dv=None, dsum=None,
-              dbq=None, dbk=None, dbv=None):
+              dbq=None, dbk=None, dbv=None, dq_accum=None):
     """dbq/dbk/dbv (fp32 [H*dh], backward): += column sums of dq/dk/dv = the in-projection's bias gradient."""
     a = K.AttnArgs()
     a.dbq, a.dbk, a.dbv = _p(dbq), _p(dbk), _p(dbv)
@@ -196,12 +196,14 @@ def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0,
     a.causal, a.q_pos0 = int(causal), q_pos0
     a.scale = 1.0 / math.sqrt(dh)
     a.dropout_p, a.seed, a.site = dropout_p, seed, site
+    a.dq_accum = _p(dq_accum)
+    a._keep = dq_accum
     return a
 
 
 def _attn_tc_ok(a) -> bool:
     return (_TC_ATTN == "tc" and a.dtype == K.BF16 and a.dh == 64 and not a.add_mask and a.q_pos0 == 0
-            and (not a.causal or a.Lq == a.Lk) and a.Lk <= 16384
+            and (not a.causal or a.Lq == a.Lk) and a.Lk <= 16384 and a.dropout_p <= 0.45
             and all(x % 8 == 0 for x in (a.ldq, a.ldk, a.ldv, a.ldo))
             and all((x or 0) % 16 == 0 for x in (a.q, a.k, a.v, a.o)))
 
@@ -222,7 +224,11 @@ def attn_fwd(a):
 
 def attn_bwd(a):
     tc = _attn_tc_ok(a) and ATTN_TC_BWD
-    with _Timed("attn_bwd", 2.0 * _attn_flops(a), 2 if tc else 3):      # tc: dQ (+dsum) and dK/dV kernels
+    if tc and not a.dq_accum:
+        # fp32 accumulation buffer of the fused backward (dQ partial sums of the key-tile CTAs)
+        a._keep = torch.empty(a.B * a.Lq, a.H * a.dh, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        a.dq_accum = a._keep.data_ptr()
+    with _Timed("attn_bwd", 2.0 * _attn_flops(a), 3 if tc else 3):      # tc: D = rowsum(dO o O), fused dQ/dK/dV, dQ convert
         if tc:
             K.check(K.lib().smer_attn_bwd_tc(C.byref(a), K.stream()), "attn_bwd_tc")
         else:
