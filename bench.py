@@ -793,7 +793,7 @@ def main():
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--ff", type=int, default=2048)
     args = ap.parse_args()
-    args.skip = set(x for x in args.skip.split(",") if x)
+    args.skip = set(x for x in args.skip.replace("+", ",").split(",") if x)
     CFG.update(d=args.d_model, nhead=args.nhead, le=args.layers, ld=args.layers, ff=args.ff,
                max_len=max(2400, args.seq, args.tgt))
     if args.warmup < 3 and args.impl == "ours" and args.workload == "train":

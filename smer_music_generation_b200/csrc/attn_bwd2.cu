@@ -13,9 +13,12 @@
 //                                   written once by the threads: MN-major view for dV / dK, K-major view for dQ)
 //   warps 0..15  element-wise work, TMEM lane = query row; warpgroup g owns key columns [32g, 32g+32) of the tile:
 //                P = exp2(S c - lse), keep mask, Pd = P keep/(1-p) (bf16), dS = P (dP keep/(1-p) - D) (bf16) -> registers;
-//                then (once the previous tile's MMAs are done) drain its share of dQ_{n-1} with fp32 red.global.add
-//                into the accumulation buffer, store Pd / dS to shared memory and hand them to the MMA warp.
-//   warps 18,19  idle (roles are warpgroup-aligned for setmaxnreg).
+//                then (once the previous tile's MMAs are done) move its share of dQ_{n-1} from TMEM to a shared-memory
+//                staging tile, store Pd / dS to shared memory and hand them to the MMA warp.
+//   warp 18      dQ reducer: when the staging tile is complete, ONE bulk reduction (cp.reduce.async.bulk.tensor .add,
+//                fp32) adds it to the accumulation buffer in L2 -- per-thread red.global.add.v4 of the same data kept
+//                the LSU busy for ~40 % of the kernel.
+//   warp 19      idle (roles are warpgroup-aligned for setmaxnreg).
 // D = rowsum(dO o O) comes from a small pre-kernel; dQ accumulates across the key-tile CTAs in an fp32 buffer and a
 // post-kernel scales / converts it to bf16 and reduces the in-projection's Q-bias gradient.
 #include <type_traits>
@@ -26,6 +29,8 @@
 
 int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
                         int box_inner, int box_outer);
+int smer_make_tmap_f32(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
+                       int box_inner, int box_outer);
 
 namespace {
 
@@ -33,7 +38,8 @@ constexpr int BM = 128, BN = 128, DH = 64;
 constexpr int TILE = BM * DH * 2;                 // 16 KB
 constexpr int THREADS = 640;
 constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE /*[2]*/, OFF_DO = 4 * TILE /*[2]*/, OFF_P = 6 * TILE /*32 KB*/,
-              OFF_DS = 8 * TILE /*32 KB*/, OFF_BAR = 10 * TILE;
+              OFF_DS = 8 * TILE /*32 KB*/, OFF_DQ = 10 * TILE /*32 KB: [2 column halves][128 rows][32 fp32], swizzled*/,
+              OFF_BAR = 12 * TILE;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 320, COL_DQ = 384;
@@ -71,13 +77,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, Params p) {
+                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ CUtensorMap tmDQ, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *sdp_full = bars + 5,
-           *sdp_free = bars + 6, *pds_full = bars + 7, *mma3_done = bars + 8;
-  constexpr int NBARS = 9;
+           *sdp_free = bars + 6, *pds_full = bars + 7, *mma3_done = bars + 8, *dqs_full = bars + 9, *dqs_free = bars + 10;
+  constexpr int NBARS = 11;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +97,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 16 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmdO); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    for (int i = 0; i < NBARS; ++i) ptx::mbar_init(bars + i, (i == 6 || i == 7) ? 16 : 1);
+    for (int i = 0; i < NBARS; ++i) ptx::mbar_init(bars + i, (i == 6 || i == 7 || i == 9) ? 16 : 1);
     ptx::fence_barrier_init();
   }
   if (warp == 17) ptx::tmem_alloc<TMEM_COLS>(tmem_ptr);
@@ -168,6 +175,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
       __syncwarp();
+    } else if (warp == 18) {
+      // ---------------------------------------------------------------- dQ reducer
+      if (ptx::elect_one()) {
+        for (int n = 0; n < ntiles; ++n) {
+          ptx::mbar_wait(dqs_full, n & 1);              // all 16 warps have written dQ_n to the staging tile
+          const int row0 = b * p.Lq + (it0 + n) * BM;
+          ptx::tma_reduce_add_2d(&tmDQ, smem + OFF_DQ, h * DH, row0);
+          ptx::tma_reduce_add_2d(&tmDQ, smem + OFF_DQ + TILE, h * DH + 32, row0);
+          ptx::tma_commit_group();
+          ptx::tma_wait_group_read0();                  // the staging tile has been read
+          ptx::mbar_arrive(dqs_free);
+        }
+        ptx::tma_wait_group0();                         // reductions performed before the CTA retires
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ element-wise threads
@@ -181,6 +203,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t row_off = (uint32_t)(g >> 1) * TILE + (uint32_t)r * 128;
     const uint32_t aP_row = ptx::smem_u32(smem + OFF_P) + row_off, aDS_row = ptx::smem_u32(smem + OFF_DS) + row_off;
     const uint32_t c16_0 = (uint32_t)(g & 1) * 4;
+    // dQ staging: column half (g >> 1) holds dQ columns [32 (g >> 1), +32) as 128-byte rows; this thread's 16 columns are
+    // the 16-byte chunks 4 (g & 1) .. +3 of row r
+    const uint32_t aDQ_row = ptx::smem_u32(smem + OFF_DQ) + (uint32_t)(g >> 1) * TILE + (uint32_t)r * 128;
     // key mask of this thread's 32 keys: padding / beyond kend (constant over the query tiles)
     uint32_t kmask = 0u;
     {
@@ -191,16 +216,22 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float c2 = p.c_log2;
     const long long rowbase = ((long long)b * p.H + h) * p.Lq;
     const uint32_t sitekey = DROP ? attn_site_key(eff_seed(p.seed, p.seed_dev), p.site) : 0u;
-    int prev_i = -1;                                  // query row whose dQ sits in TMEM (previous tile)
+    // per-row constants of a query tile are fetched one tile ahead (their global-load latency is off the critical path)
+    float lse_nx = -INFINITY, dsum_nx = 0.f;
+    if (ntiles > 0 && it0 * BM + r < p.Lq) {
+      lse_nx = p.lse[rowbase + it0 * BM + r];
+      dsum_nx = p.dsum[rowbase + it0 * BM + r];
+    }
     for (int n = 0; n < ntiles; ++n) {
       const int iq0 = (it0 + n) * BM;
       const int i = iq0 + r;
       const bool row_ok = i < p.Lq;
-      float lse2 = INFINITY, dsum = 0.f;              // invalid rows: P = exp2(-inf) = 0
-      if (row_ok) {
-        const float l = p.lse[rowbase + i];
-        lse2 = l == -INFINITY ? INFINITY : l * 1.4426950408889634f;
-        dsum = p.dsum[rowbase + i];
+      // invalid rows: lse = -inf -> P = exp2(-inf) = 0
+      const float lse2 = (!row_ok || lse_nx == -INFINITY) ? INFINITY : lse_nx * 1.4426950408889634f;
+      const float dsum = row_ok ? dsum_nx : 0.f;
+      if (n + 1 < ntiles && i + BM < p.Lq) {
+        lse_nx = p.lse[rowbase + i + BM];
+        dsum_nx = p.dsum[rowbase + i + BM];
       }
       const int ii = row_ok ? i : p.Lq - 1;
       const uint32_t rowkey = DROP ? attn_row_key(sitekey, rowbase + ii) : 0u;
@@ -218,7 +249,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(sdp_free);       // S / dP may be overwritten by the next tile's MMAs
+      if (lane == 0) ptx::mbar_arrive_relaxed(sdp_free);   // S / dP may be overwritten by the next tile's MMAs
       if (masked) {
 #pragma unroll
         for (int k = 0; k < 32; ++k)
@@ -256,44 +287,46 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       (void)ik2;
       // ---- the previous tile's MMAs are done: its dQ can be drained, and Pd / dS shared memory may be rewritten
       if (n > 0) {
+        // dQ_{n-1}: TMEM -> swizzled fp32 staging tile (this warpgroup's 16 columns of row r), reduced into the
+        // accumulation buffer by warp 18's bulk reduction
         ptx::mbar_wait(mma3_done, (n - 1) & 1);
         ptx::tc_fence_after();
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(lane_base + COL_DQ + g * 16, v);
-        ptx::tmem_ld_wait(v);
-        ptx::tc_fence_before();
-        if (prev_i >= 0) {
-          float* dst = p.dq_acc + ((long long)b * p.Lq + prev_i) * ((long long)p.H * DH) + h * DH + g * 16;
+        uint32_t dqv[16];
+        ptx::tmem_ld_32x16(lane_base + COL_DQ + g * 16, dqv);
+        ptx::tmem_ld_wait(dqv);
+        if (n > 1) ptx::mbar_wait(dqs_free, (n - 2) & 1);          // the reducer has read dQ_{n-2} out of the staging tile
 #pragma unroll
-          for (int k = 0; k < 16; k += 4)
-            red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-        }
+        for (int c = 0; c < 4; ++c)
+          st_shared_v4(aDQ_row + ((((uint32_t)(g & 1) * 4 + c) ^ rx) << 4), dqv[c * 4], dqv[c * 4 + 1], dqv[c * 4 + 2], dqv[c * 4 + 3]);
       }
-      prev_i = row_ok ? i : -1;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t off = ((c16_0 + (uint32_t)c) ^ rx) << 4;
         st_shared_v4(aP_row + off, pd[c * 4], pd[c * 4 + 1], pd[c * 4 + 2], pd[c * 4 + 3]);
         st_shared_v4(aDS_row + off, ds[c * 4], ds[c * 4 + 1], ds[c * 4 + 2], ds[c * 4 + 3]);
       }
-      ptx::fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core
+      ptx::fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core / TMA
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(pds_full);
+      if (lane == 0) {
+        if (n > 0) ptx::mbar_arrive(dqs_full);
+        ptx::mbar_arrive(pds_full);
+      }
     }
     // ---- last tile's dQ, then dK / dV of this CTA's 128 keys
     if (ntiles > 0) {
       ptx::mbar_wait(mma3_done, (ntiles - 1) & 1);
       ptx::tc_fence_after();
-      uint32_t v[16];
-      ptx::tmem_ld_32x16(lane_base + COL_DQ + g * 16, v);
-      ptx::tmem_ld_wait(v);
-      if (prev_i >= 0) {
-        float* dst = p.dq_acc + ((long long)b * p.Lq + prev_i) * ((long long)p.H * DH) + h * DH + g * 16;
+      uint32_t dqv[16];
+      ptx::tmem_ld_32x16(lane_base + COL_DQ + g * 16, dqv);
+      ptx::tmem_ld_wait(dqv);
+      if (ntiles > 1) ptx::mbar_wait(dqs_free, (ntiles - 2) & 1);
 #pragma unroll
-        for (int k = 0; k < 16; k += 4)
-          red_add_v4(dst + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
-      }
+      for (int c = 0; c < 4; ++c)
+        st_shared_v4(aDQ_row + ((((uint32_t)(g & 1) * 4 + c) ^ rx) << 4), dqv[c * 4], dqv[c * 4 + 1], dqv[c * 4 + 2], dqv[c * 4 + 3]);
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dqs_full);
     }
     const int j = j0 + r;                              // TMEM lane = key row for dK / dV
     const bool key_ok = j < p.Lk;
@@ -438,7 +471,8 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
     SMER_CUDA(cudaFuncSetAttribute(attn_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_dev_mask |= 1 << dev;
   }
-  CUtensorMap tq, tdo, tk, tv;
+  CUtensorMap tq, tdo, tk, tv, tdq;
+  if ((rc = smer_make_tmap_f32(&tdq, a->dq_accum, dcols, rq, dcols, 32, BM))) return rc;
   if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, rq, a->ldq, DH, BM))) return rc;
   if ((rc = smer_make_tmap_bf16(&tdo, a->dout, dcols, rq, a->lddo, DH, BM))) return rc;
   if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, rk, a->ldk, DH, BN))) return rc;
@@ -450,8 +484,8 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
                                                                         a->dsum, a->B, a->H, a->Lq);
   }
   dim3 grid((a->Lk + BN - 1) / BN, a->H, a->B);
-  if (p.thr2) attn_bwd2_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
-  else attn_bwd2_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
+  if (p.thr2) attn_bwd2_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tk, tv, tdq, p);
+  else attn_bwd2_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tk, tv, tdq, p);
   {
     dim3 g2((unsigned)((rq + 63) / 64), (unsigned)((dcols + 255) / 256));
     attn_dq_finish_kernel<<<g2, 256, 0, st>>>((const float*)a->dq_accum, (bf16*)a->dq, a->lddq, a->dbq, rq, (int)dcols, a->scale);

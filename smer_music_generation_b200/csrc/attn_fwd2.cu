@@ -350,7 +350,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         ptx::tc_fence_before();                      // orders this thread's tcgen05.ld / st before the MMAs that follow the arrive
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(p_full + q);
+        if (lane == 0) ptx::mbar_arrive_relaxed(p_full + q);     // P went through tensor memory: the tcgen05 fences order it
       }
       // ---- epilogue of the item: merge the two key halves of the row, O / l -> global
       // this thread stores output columns [32 hf, 32 hf + 32); the other 32 columns of its partial go to the peer

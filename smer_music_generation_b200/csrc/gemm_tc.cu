@@ -477,6 +477,31 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
   return SMER_OK;
 }
 
+// fp32 tensor map (SWIZZLE_128B, 32 floats = 128 bytes inner box): the dQ accumulation buffer of the fused attention
+// backward, the target of cp.reduce.async.bulk.tensor (not cached: one map per launch)
+int smer_make_tmap_f32(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
+                       int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { smer_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return SMER_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch * 4) % 16) {
+    smer_set_error("TMA operand needs a 16-byte aligned base and pitch (ptr=%p pitch=%lld elements)", ptr, pitch);
+    return SMER_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    smer_set_error("cuTensorMapEncodeTiled(f32) failed (%d) inner=%lld outer=%lld pitch=%lld box=%dx%d", (int)r, inner, outer,
+                   pitch, box_inner, box_outer);
+    return SMER_ERR_CUDA;
+  }
+  return SMER_OK;
+}
+
 template <bool A_MN, bool B_MN, typename TC, int BN, int EPI, int CTAS = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
