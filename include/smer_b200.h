@@ -102,7 +102,8 @@ typedef struct smer_attn_args {
   float* lse;                 /* [B,H,Lq] log-sum-exp of the masked scaled scores             */
   float* dsum;                /* [B,H,Lq] backward scratch: rowsum(dO*O)                      */
   const uint8_t* key_pad;     /* [B,Lk], 1 = key masked (key_padding_mask) or NULL            */
-  const int* kv_len;          /* [B] 1+last unmasked key (loop bound) or NULL                 */
+  const int* kv_len;          /* [B] |v| = 1+last unmasked key (loop bound) or NULL; v >= 0 asserts that the mask is a
+                                 pure suffix (key j masked <=> j >= v: key_pad is not read), v < 0: it has holes */
   const float* add_mask;      /* [Lq,Lk] additive float mask or NULL (simt kernels only)      */
   long long ld_mask;
   int B, H, Lq, Lk, dh;
@@ -222,6 +223,7 @@ int smer_sample_masked(const smer_sample_args* a, void* stream);
 int smer_cast2d(const void* src, int src_dtype, long long src_ld, void* dst, int dst_dtype, long long dst_ld,
                 long long rows, int cols, int dst_cols, void* stream);
 int smer_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* kv_len[b] = +(1+last unmasked key) when the masked keys of row b are a pure suffix, -(1+last unmasked key) otherwise */
 int smer_kv_len_from_pad(const uint8_t* pad, int* kv_len, int B, int L, void* stream);
 /* flags3 (device int[3]): [0] bad lower triangle, [1] some upper entry != -inf, [2] some upper entry != 0 */
 int smer_classify_mask(const float* mask, long long ld, int T, int* flags3, void* stream);

@@ -90,7 +90,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int j0 = blockIdx.x * BN;                    // first key of this CTA
-  const int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  const int klen = p.kv_len ? p.kv_len[b] : p.Lk;    // < 0: the key mask has holes (common.cuh / smer_b200.h)
+  const int kend = min(abs(klen), p.Lk);
+  const bool read_pad = p.pad != nullptr && (klen < 0 || p.kv_len == nullptr);
   const int nqt = (p.Lq + BM - 1) / BM;
   const int it0 = p.causal ? j0 / BM : 0;            // causal: queries i >= j0 only
   const int ntiles = j0 < kend ? max(0, nqt - it0) : 0;
@@ -210,7 +212,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint32_t kmask = 0u;
     {
       const int jj = j0 + g * 32 + lane;
-      const bool msk = jj >= kend || (p.pad && jj < p.Lk && p.pad[(long long)b * p.Lk + jj]);
+      const bool msk = jj >= kend || (read_pad && jj < p.Lk && p.pad[(long long)b * p.Lk + jj]);
       kmask = __ballot_sync(0xffffffffu, msk);
     }
     const float c2 = p.c_log2;

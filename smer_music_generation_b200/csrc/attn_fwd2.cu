@@ -35,11 +35,9 @@ constexpr int KS = 3;                             // K and V ring depth
 constexpr int NCHAIN = 4;
 constexpr int THREADS = 640;                      // 4 softmax warpgroups + 1 producer warpgroup (TMA warp, MMA warp, 2 idle)
 constexpr int MASK_WORDS = 512;                   // key-mask bitmap of one batch row: Lk <= 16384
-constexpr int XCH_STRIDE = 33;                    // floats per row of the merge exchange (padded: conflict-free)
 constexpr int OFF_K = 2 * TILE, OFF_V = OFF_K + KS * TILE, OFF_BAR = OFF_V + KS * TILE;
 constexpr int OFF_MASK = OFF_BAR + 256;
-constexpr int OFF_XCH = OFF_MASK + 2 * MASK_WORDS * 4;               // [2 query tiles][2 halves][128 rows][33] fp32
-constexpr int OFF_ML = OFF_XCH + 2 * 2 * BM * XCH_STRIDE * 4;        // [2][2][128][2] fp32: (m, l) of every chain row
+constexpr int OFF_ML = OFF_MASK + 2 * MASK_WORDS * 4;                // [2 query tiles][2 halves][128][2] fp32: (m, l) of every chain row
 constexpr int SMEM_BYTES = OFF_ML + 2 * 2 * BM * 2 * 4 + 1024 /*alignment slack*/;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_O = 256;        // S_q at COL_S + 64 q, O_q at COL_O + 64 q, P_q over S_q's first 32 columns
@@ -78,6 +76,8 @@ struct Item {
   int nt0, nt1;            // 128-key K/V tiles of query tile 0 / 1 (0: tile inactive)
   int kend0, kend1;
   int ntk;                 // K / V tiles to load = max
+  int klen;                // kv_len[b] clipped to Lk (before the causal bound)
+  bool holes;              // the key mask is not a pure suffix: key_pad has to be read
 };
 
 __device__ __forceinline__ Item item_of(const Params& p, int item) {
@@ -89,7 +89,10 @@ __device__ __forceinline__ Item item_of(const Params& p, int item) {
   it.h = rem % p.H;
   it.b = rem / p.H;
   it.i0 = qp * 2 * BM;
-  const int kl = p.kv_len ? min(p.kv_len[it.b], p.Lk) : p.Lk;
+  const int kraw = p.kv_len ? p.kv_len[it.b] : p.Lk;
+  const int kl = min(abs(kraw), p.Lk);
+  it.klen = kl;
+  it.holes = p.pad != nullptr && (kraw < 0 || p.kv_len == nullptr);
   int ke0 = it.i0 < p.Lq ? kl : 0, ke1 = it.i0 + BM < p.Lq ? kl : 0;
   if (p.causal) { ke0 = min(ke0, it.i0 + BM); ke1 = min(ke1, it.i0 + 2 * BM); }
   it.kend0 = ke0; it.kend1 = ke1;
@@ -234,8 +237,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t tS = lane_base + COL_S + q * 64, tO = lane_base + COL_O + q * 64;
     const uint32_t a_mask = ptx::smem_u32(smem + OFF_MASK) + c * MASK_WORDS * 4;
-    const uint32_t a_xch_mine = ptx::smem_u32(smem + OFF_XCH) + ((c * 2 + hf) * BM + r) * XCH_STRIDE * 4;
-    const uint32_t a_xch_peer = ptx::smem_u32(smem + OFF_XCH) + ((c * 2 + (hf ^ 1)) * BM + r) * XCH_STRIDE * 4;
     const uint32_t a_ml_mine = ptx::smem_u32(smem + OFF_ML) + ((c * 2 + hf) * BM + r) * 8;
     const uint32_t a_ml_peer = ptx::smem_u32(smem + OFF_ML) + ((c * 2 + (hf ^ 1)) * BM + r) * 8;
     const float c2 = p.c_log2;
@@ -250,24 +251,31 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int ii = row_ok ? i : p.Lq - 1;
       const long long rowid = ((long long)it.b * p.H + it.h) * p.Lq + ii;
       const uint32_t rowkey = DROP ? attn_row_key(sitekey, rowid) : 0u;
-      // key-mask bitmap of this item's tiles (bit j: key j masked), built once per item by the query tile's 256 threads
-      const bool use_mask = nt > 0 && (p.pad != nullptr || (kend & (BN - 1)) != 0);
-      bar_sync_qtile(c);                             // every thread of the query tile has left the previous item's bitmap / exchange
-      if (use_mask) {
+      // Masked keys: a pure suffix (the reference's padding, and every kv_len bound) is handled arithmetically below;
+      // only a mask with holes needs the per-key bytes: its bitmap (bit j: key j masked) is built once per item by the
+      // query tile's 256 threads.
+      const bool use_bitmap = nt > 0 && it.holes;
+      const bool tail_mask = nt > 0 && (kend & (BN - 1)) != 0 && kend == it.klen;     // the last tile crosses kv_len
+      bar_sync_qtile(c);                             // every thread of the query tile has left the previous item (O, bitmap, m/l)
+      if (use_bitmap) {
         for (int j = (hf * 4 + quarter) * 32 + lane; j < nt * BN; j += 256) {
-          const bool msk = j >= kend || (p.pad && p.pad[(long long)it.b * p.Lk + j]);
+          const bool msk = j >= kend || p.pad[(long long)it.b * p.Lk + j];
           const uint32_t bal = __ballot_sync(0xffffffffu, msk);
           if (lane == 0) sts_u(a_mask + (j >> 5) * 4, bal);
         }
+        bar_sync_qtile(c);                           // publishes the bitmap
       }
-      bar_sync_qtile(c);                             // publishes the bitmap
       float m = -INFINITY, l = 0.f;                  // reference maximum (log2 units, may lag) and row sum of this key half
       for (int t = 0; t < nt; ++t, ++ns) {
         const int j0 = t * BN + hf * BH;             // first key of this chain's half of the tile
         uint32_t mw0 = 0u, mw1 = 0u;
-        if (use_mask) {
+        if (use_bitmap) {
           mw0 = lds_u(a_mask + ((j0 >> 5)) * 4);
           mw1 = lds_u(a_mask + ((j0 >> 5) + 1) * 4);
+        } else if (tail_mask && j0 + BH > kend) {
+          const int nv0 = kend - j0, nv1 = kend - (j0 + 32);
+          mw0 = nv0 <= 0 ? 0xffffffffu : (nv0 >= 32 ? 0u : (0xffffffffu << nv0));
+          mw1 = nv1 <= 0 ? 0xffffffffu : (nv1 >= 32 ? 0u : (0xffffffffu << nv1));
         }
         if (p.causal && j0 + BH - 1 > r0) {
           const int nv0 = i - j0 + 1, nv1 = i - (j0 + 32) + 1;
@@ -352,51 +360,48 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_relaxed(p_full + q);     // P went through tensor memory: the tcgen05 fences order it
       }
-      // ---- epilogue of the item: merge the two key halves of the row, O / l -> global
-      // this thread stores output columns [32 hf, 32 hf + 32); the other 32 columns of its partial go to the peer
-      float mine[32];
-      if (nt > 0) {                                  // uniform over the query tile's threads
-        ptx::mbar_wait(o_full + q, no & 1);
-        ++no;
-        ptx::tc_fence_after();
-        uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32(tO + hf * 32, v0);        // the columns this thread finishes
-        ptx::tmem_ld_32x32(tO + (hf ^ 1) * 32, v1);  // the columns the peer finishes
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          mine[k] = __uint_as_float(v0[k]);
-          sts_f(a_xch_mine + k * 4, __uint_as_float(v1[k]));
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) mine[k] = 0.f;
-      }
+      // ---- epilogue of the item: merge the two key halves of the row, O / l -> global.  Both halves' accumulators sit
+      // in this thread's TMEM lane (O_{2c} and O_{2c+1}), so only (m, l) travel through shared memory; this thread
+      // finishes output columns [32 hf, 32 hf + 32).
       sts_f(a_ml_mine, m);
       sts_f(a_ml_mine + 4, l);
-      bar_sync_qtile(c);
-      if (nt > 0 && row_ok) {
+      if (nt > 0) {                                  // uniform over the query tile's threads
+        ptx::mbar_wait(o_full + 2 * c, no & 1);      // both chains' last PV MMAs have completed
+        ptx::mbar_wait(o_full + 2 * c + 1, no & 1);
+        ++no;
+        ptx::tc_fence_after();
+      }
+      bar_sync_qtile(c);                             // (m, l) of both halves are published
+      if (nt > 0) {
+        const uint32_t tOa = lane_base + COL_O + (2 * c) * 64 + hf * 32, tOb = tOa + 64;
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32(tOa, va);
+        ptx::tmem_ld_32x32(tOb, vb);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
         const float mp = lds_f(a_ml_peer), lp = lds_f(a_ml_peer + 4);
-        const float mm = fmaxf(m, mp);
-        const float fa = m == -INFINITY ? 0.f : ex2(m - mm), fb = mp == -INFINITY ? 0.f : ex2(mp - mm);
-        const float lt = l * fa + lp * fb;
+        const float ma = hf ? mp : m, mb = hf ? m : mp, la = hf ? lp : l, lb = hf ? l : lp;
+        const float mm = fmaxf(ma, mb);
+        const float fa = ma == -INFINITY ? 0.f : ex2(ma - mm), fb = mb == -INFINITY ? 0.f : ex2(mb - mm);
+        const float lt = la * fa + lb * fb;
         const float inv = lt > 0.f ? p.inv_keep / lt : 0.f;      // dropout's 1/(1-p) applied once per row
         const float wa = fa * inv, wb = fb * inv;
-        bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
+        if (row_ok) {
+          bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
 #pragma unroll
-        for (int k = 0; k < 32; k += 8) {
-          float f[8];
+          for (int k = 0; k < 32; k += 8) {
+            float f[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) f[u] = mine[k + u] * wa + lds_f(a_xch_peer + (k + u) * 4) * wb;
-          uint4 u4;
-          u4.x = pack_bf16x2(f[0], f[1]);
-          u4.y = pack_bf16x2(f[2], f[3]);
-          u4.z = pack_bf16x2(f[4], f[5]);
-          u4.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + k) = u4;
+            for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(va[k + u]) * wa + __uint_as_float(vb[k + u]) * wb;
+            uint4 u4;
+            u4.x = pack_bf16x2(f[0], f[1]);
+            u4.y = pack_bf16x2(f[2], f[3]);
+            u4.z = pack_bf16x2(f[4], f[5]);
+            u4.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(orow + k) = u4;
+          }
+          if (p.lse && hf == 0) p.lse[rowid] = lt > 0.f ? (mm + log2f(lt)) * 0.6931471805599453f : -INFINITY;
         }
-        if (p.lse && hf == 0) p.lse[rowid] = lt > 0.f ? (mm + log2f(lt)) * 0.6931471805599453f : -INFINITY;
       } else if (row_ok) {                           // no visible key at all: zeros (uniform branch per query tile)
         bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
 #pragma unroll

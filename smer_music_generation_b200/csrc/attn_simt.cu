@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_fwd_simt_kernel(AttnParams p) {
     acc[c] = 0.f;
   }
   float m = -INFINITY, l = 0.f;
-  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  int kend = p.kv_len ? min(abs(p.kv_len[b]), p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
   const uint32_t rowkey = p.thr ? attn_row_key(attn_site_key(eff_seed(p.seed, p.seed_dev), p.site), rowid) : 0u;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dq_kernel(AttnParams p) {
   long long rowid = ((long long)b * p.H + h) * p.Lq + ic;
   float lse = p.lse[rowid], dsum = p.dsum[rowid];
   const uint32_t rowkey = p.thr ? attn_row_key(attn_site_key(eff_seed(p.seed, p.seed_dev), p.site), rowid) : 0u;
-  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  int kend = p.kv_len ? min(abs(p.kv_len[b]), p.Lk) : p.Lk;
   if (p.causal) kend = min(kend, min(p.Lq, (int)(blockIdx.x + 1) * ROWS) + p.q_pos0);
   const T* kb = (const T*)p.k + (long long)b * p.Lk * p.ldk + h * DH;
   const T* vb = (const T*)p.v + (long long)b * p.Lk * p.ldv + h * DH;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS) attn_bwd_dkv_kernel(AttnParams p) {
     vr[c] = to_f32(vp[c]);
     dk[c] = dv[c] = 0.f;
   }
-  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  int kend = p.kv_len ? min(abs(p.kv_len[b]), p.Lk) : p.Lk;
   bool key_masked = !row_ok || j >= kend || (p.pad && p.pad[(long long)b * p.Lk + jc]);
   int istart = p.causal ? max(0, (int)(blockIdx.x * ROWS) - p.q_pos0) / KT * KT : 0;     // queries i >= first key of the block
   const T* qb = (const T*)p.q + (long long)b * p.Lq * p.ldq + h * DH;
@@ -354,7 +354,7 @@ template <typename T, int DH>
 __global__ void __launch_bounds__(NTHREADS) attn_weights_kernel(AttnParams p, float* __restrict__ w, long long ldw) {
   int b = blockIdx.z;
   int i = blockIdx.y;
-  int kend = p.kv_len ? min(p.kv_len[b], p.Lk) : p.Lk;
+  int kend = p.kv_len ? min(abs(p.kv_len[b]), p.Lk) : p.Lk;
   for (int j = blockIdx.x * NTHREADS + threadIdx.x; j < p.Lk; j += gridDim.x * NTHREADS) {
     bool masked = j >= kend || (p.pad && p.pad[(long long)b * p.Lk + j]) || (p.causal && j > i + p.q_pos0);
     float acc = 0.f;

@@ -254,22 +254,27 @@ extern "C" int smer_colsum(const void* x, int dtype, long long ld, float* out, l
 }
 
 // ---------------------------------------------------------------------------------------
-// Mask inspection.  kv_len[b] = 1 + index of the last un-padded key (A0: pads are a suffix,
-// but the attention kernels still honour the per-key mask; kv_len only bounds the key loop).
+// Mask inspection.  |kv_len[b]| = 1 + index of the last un-padded key; it bounds the key loop of the attention
+// kernels.  The SIGN tells them whether the mask is a pure suffix (>= 0: key j masked <=> j >= kv_len[b], which is how
+// the reference's collate functions pad, dataset.py:783-784,828 -- no per-key mask reads needed) or has masked keys
+// before its last visible one (< 0: the kernels consult key_pad).
 // ---------------------------------------------------------------------------------------
 __global__ void kv_len_kernel(const uint8_t* __restrict__ pad, int* __restrict__ kv_len, int L) {
   int b = blockIdx.x;
-  int best = 0;
+  int best = 0, cnt = 0;
   for (int j = threadIdx.x; j < L; j += blockDim.x)
-    if (!pad[(long long)b * L + j]) best = j + 1;
-  __shared__ int sm[32];
-  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+    if (!pad[(long long)b * L + j]) { best = j + 1; ++cnt; }
+  __shared__ int sm[32], sc[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = best; sc[threadIdx.x >> 5] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int m = 0;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = max(m, sm[w]);
-    kv_len[b] = m;
+    int m = 0, c = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) { m = max(m, sm[w]); c += sc[w]; }
+    kv_len[b] = c == m ? m : -m;
   }
 }
 

@@ -341,7 +341,11 @@ def test_attention_tc_vs_simt_and_torch(dev, Lq, Lk, causal, use_pad, drop):
         pad = (torch.arange(Lk)[None] >= lens[:, None]).to(torch.uint8).to(dev)
         if not causal:
             pad[1, Lk // 3] = 1                  # a non-suffix masked key: honoured through the per-key mask
-        kv_len = lens.to(torch.int32).to(dev)
+        # the loop bound comes from the library's own helper: its sign says whether the mask is a pure suffix (row 0)
+        # or has holes (row 1 of the non-causal cases) -- include/smer_b200.h
+        kv_len = torch.empty(B, dtype=torch.int32, device=dev)
+        ops.kv_len_from_pad(pad, kv_len)
+        assert kv_len.tolist() == [int(lens[0]), int(lens[1]) if causal else -int(lens[1])]
     outs = {}
     for path in ("tc", "simt"):
         ops._TC_ATTN = path
