@@ -227,16 +227,18 @@ __device__ __forceinline__ uint32_t attn_block_word(uint32_t rowkey, uint32_t jb
   x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
   return x;
 }
-// x[k] = w advanced by k LCG steps, k = 0..7: the pair words of the block's 16 keys (7 independent multiply-adds)
+// x[k] = w advanced by k LCG steps, k = 0..7: the pair words of the block's 16 keys, as a depth-3 tree of
+// multiply-adds with only three distinct multipliers (registers are what the softmax threads are short of)
 __device__ __forceinline__ void attn_pair_words(uint32_t w, uint32_t (&x)[8]) {
+  constexpr uint32_t M1 = lcg_mul_n(1), A1 = lcg_add_n(1), M2 = lcg_mul_n(2), A2 = lcg_add_n(2), M4 = lcg_mul_n(4), A4 = lcg_add_n(4);
   x[0] = w;
-  x[1] = w * lcg_mul_n(1) + lcg_add_n(1);
-  x[2] = w * lcg_mul_n(2) + lcg_add_n(2);
-  x[3] = w * lcg_mul_n(3) + lcg_add_n(3);
-  x[4] = w * lcg_mul_n(4) + lcg_add_n(4);
-  x[5] = w * lcg_mul_n(5) + lcg_add_n(5);
-  x[6] = w * lcg_mul_n(6) + lcg_add_n(6);
-  x[7] = w * lcg_mul_n(7) + lcg_add_n(7);
+  x[1] = w * M1 + A1;
+  x[2] = w * M2 + A2;
+  x[4] = w * M4 + A4;
+  x[3] = x[2] * M1 + A1;
+  x[5] = x[4] * M1 + A1;
+  x[6] = x[4] * M2 + A2;
+  x[7] = x[6] * M1 + A1;
 }
 // packed rule: 0xFFFF in every half of `pairword` that is kept (thr2 = thr | thr << 16)
 __device__ __forceinline__ uint32_t attn_keep_mask2(uint32_t pairword, uint32_t thr2) {
