@@ -59,6 +59,17 @@ int smer_set_seed_device_ptr(const uint64_t* dev_counter);
 int smer_embed_pe_fwd(const int64_t* ids, const float* emb, const float* pe, void* out, int out_dtype,
                       int B, int L, int d, int V, int pos0, float scale, float dropout_p, uint64_t seed,
                       uint64_t site, void* stream);
+/* the same for packed rows with explicit positions: out[r] = dropout(emb[ids[r]] * scale + pe[pos[r]]) */
+int smer_embed_pe_packed(const int64_t* ids, const int* pos, const float* emb, const float* pe, void* out, int out_dtype,
+                         long long rows, int d, int V, float scale, float dropout_p, uint64_t seed, uint64_t site,
+                         void* stream);
+/* On-GPU collate of a padded batch into packed rows (dataset.py:802-925 pads; this removes the pads again):
+ * out_ids[cu[b] + l] = ids[b, l], out_pos[cu[b] + l] = l for l < cu[b+1] - cu[b]; rows in [cu[B], rows_alloc) get id 0. */
+int smer_pack_rows(const int64_t* ids, const int* cu, int B, int L, long long rows_alloc, int64_t* out_ids, int* out_pos,
+                   void* stream);
+/* rows [first_row_dev[0], rows) of a contiguous row-major buffer := 0: the ghost rows past the last sequence of a packed
+ * batch, which no attention kernel writes (first_row_dev = &cu[B], DEVICE memory, so a captured step needs no host value) */
+int smer_zero_tail_rows(void* buf, long long row_bytes, long long rows, const int* first_row_dev, void* stream);
 /* backward of the nn.Embedding gather: demb[ids] += dout * scale * dropmask */
 int smer_embed_bwd(const int64_t* ids, const void* dout, int dtype, float* demb, int B, int L, int d, int V,
                    float scale, float dropout_p, uint64_t seed, uint64_t site, void* stream);
@@ -115,6 +126,12 @@ typedef struct smer_attn_args {
   uint64_t seed, site;
   void* dq_accum;             /* backward (tc kernels): fp32 [B*Lq, H*dh] workspace; the fused backward accumulates the
                                  unscaled dQ of all key tiles here (it is zeroed by the call) before converting to dq */
+  /* Padding-free ("varlen") layout, tc kernels only: sequence b owns query rows [cu_q[b], cu_q[b+1]) and key rows
+   * [cu_k[b], cu_k[b+1]) of the packed token-major buffers (int32 prefix sums, B+1 entries each, DEVICE memory).  Lq / Lk
+   * are then the LONGEST query / key sequence (they size the grid), kv_len / key_pad must be NULL (every key of a
+   * sequence is visible), and lse / dsum are head-major: [H, cu_q[B]].  q_rows / k_rows = the packed buffers' row counts. */
+  const int *cu_q, *cu_k;
+  long long q_rows, k_rows;
 } smer_attn_args;
 int smer_attn_fwd_simt(const smer_attn_args* a, void* stream);
 int smer_attn_bwd_simt(const smer_attn_args* a, void* stream);
@@ -174,12 +191,18 @@ typedef struct smer_decode_attn_args {
   long long ldq, ld_new, ldo, ld_cache, cache_stride, ld_pad;
   int n_seq, H, dh, cache_len, splits, dtype;
   float scale;
+  const int* done;            /* [n_seq] or NULL: pieces whose flag is set are skipped (their K/V is not streamed) */
 } smer_decode_attn_args;
 long long smer_decode_attn_workspace_bytes(int n_seq, int H, int dh, int splits);
 int smer_decode_attn(const smer_decode_attn_args* a, void* stream);
 /* ids[s] = tok_buf[s, p], pos[s] = p with p = min(fed_len[s], cur_len[s]-1) (fed_len NULL: cur_len-1) */
 int smer_decode_gather(const int64_t* tok_buf, const int* cur_len, const int* fed_len, int64_t* ids, int* pos,
                        int n_seq, int max_len, void* stream);
+/* the two steps above in one launch: out[s] = emb[tok_buf[s, p]] * scale + pe[p], pos[s] = p, p as in smer_decode_gather;
+ * rows of finished pieces (done[s] != 0, done nullable) are left untouched */
+int smer_decode_embed(const int64_t* tok_buf, const int* cur_len, const int* fed_len, const int* done, int* pos,
+                      const float* emb, const float* pe, void* out, int out_dtype, int n_seq, int max_len, int d, int V,
+                      float scale, void* stream);
 int smer_embed_step(const int64_t* ids, const int* pos, const float* emb, const float* pe, void* out,
                     int out_dtype, int n_seq, int d, int V, float scale, void* stream);
 

@@ -29,14 +29,14 @@ class AttnArgs(C.Structure):
                 ("dbq", _vp), ("dbk", _vp), ("dbv", _vp), ("ldq", _ll), ("ldk", _ll), ("ldv", _ll), ("ldo", _ll), ("lddo", _ll), ("lddq", _ll), ("lddk", _ll),
                 ("lddv", _ll), ("lse", _vp), ("dsum", _vp), ("key_pad", _vp), ("kv_len", _vp), ("add_mask", _vp),
                 ("ld_mask", _ll), ("B", _i), ("H", _i), ("Lq", _i), ("Lk", _i), ("dh", _i), ("dtype", _i),
-                ("causal", _i), ("q_pos0", _i), ("scale", _f), ("dropout_p", _f), ("seed", _u64), ("site", _u64), ("dq_accum", _vp)]
+                ("causal", _i), ("q_pos0", _i), ("scale", _f), ("dropout_p", _f), ("seed", _u64), ("site", _u64), ("dq_accum", _vp), ("cu_q", _vp), ("cu_k", _vp), ("q_rows", _ll), ("k_rows", _ll)]
 
 
 class DecodeAttnArgs(C.Structure):
     _fields_ = [("q", _vp), ("new_k", _vp), ("new_v", _vp), ("k_cache", _vp), ("v_cache", _vp), ("out", _vp),
                 ("kv_len", _vp), ("key_pad", _vp), ("workspace", _vp), ("ldq", _ll), ("ld_new", _ll), ("ldo", _ll),
                 ("ld_cache", _ll), ("cache_stride", _ll), ("ld_pad", _ll), ("n_seq", _i), ("H", _i), ("dh", _i),
-                ("cache_len", _i), ("splits", _i), ("dtype", _i), ("scale", _f)]
+                ("cache_len", _i), ("splits", _i), ("dtype", _i), ("scale", _f), ("done", _vp)]
 
 
 class SampleArgs(C.Structure):
@@ -54,6 +54,9 @@ _SIGS = {
     "smer_device_ok": (C.c_int, []),
     "smer_set_seed_device_ptr": (_i, [_vp]),
     "smer_embed_pe_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _u64, _u64, _vp]),
+    "smer_embed_pe_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _f, _u64, _u64, _vp]),
+    "smer_pack_rows": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp]),
+    "smer_zero_tail_rows": (_i, [_vp, _ll, _ll, _vp, _vp]),
     "smer_embed_bwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _f, _u64, _u64, _vp]),
     "smer_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _f, _u64, _u64, _vp]),
     "smer_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _u64, _u64, _vp]),
@@ -77,6 +80,7 @@ _SIGS = {
     "smer_decode_attn_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "smer_decode_attn": (_i, [C.POINTER(DecodeAttnArgs), _vp]),
     "smer_decode_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "smer_decode_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "smer_embed_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "smer_sample_masked": (_i, [C.POINTER(SampleArgs), _vp]),
     "smer_cast2d": (_i, [_vp, _i, _ll, _vp, _i, _ll, _ll, _i, _i, _vp]),

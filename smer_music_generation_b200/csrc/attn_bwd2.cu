@@ -60,6 +60,7 @@ struct Params {
   float inv_keep;
   uint64_t seed, site;
   const unsigned long long* seed_dev;
+  const int *cu_q, *cu_k;    // padding-free layout (smer_b200.h) or NULL
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -90,10 +91,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int j0 = blockIdx.x * BN;                    // first key of this CTA
-  const int klen = p.kv_len ? p.kv_len[b] : p.Lk;    // < 0: the key mask has holes (common.cuh / smer_b200.h)
-  const int kend = min(abs(klen), p.Lk);
+  // rows of sequence b in the Q / dO (and dq_acc) and K / V buffers, and its lse / dsum / dropout row ids
+  const int q_row0 = p.cu_q ? p.cu_q[b] : b * p.Lq, lq = p.cu_q ? p.cu_q[b + 1] - q_row0 : p.Lq;
+  const int k_row0 = p.cu_q ? p.cu_k[b] : b * p.Lk, lk = p.cu_q ? p.cu_k[b + 1] - k_row0 : p.Lk;
+  const long long rowbase = p.cu_q ? (long long)h * p.cu_q[p.B] + q_row0 : ((long long)b * p.H + h) * p.Lq;
+  const int klen = p.cu_q ? lk : (p.kv_len ? p.kv_len[b] : p.Lk);    // < 0: the key mask has holes (smer_b200.h)
+  const int kend = min(abs(klen), lk);
   const bool read_pad = p.pad != nullptr && (klen < 0 || p.kv_len == nullptr);
-  const int nqt = (p.Lq + BM - 1) / BM;
+  const int nqt = (lq + BM - 1) / BM;
   const int it0 = p.causal ? j0 / BM : 0;            // causal: queries i >= j0 only
   const int ntiles = j0 < kend ? max(0, nqt - it0) : 0;
 
@@ -114,14 +119,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // ---------------------------------------------------------------- TMA producer
       if (ptx::elect_one() && ntiles > 0) {
         ptx::mbar_expect_tx(kv_full, 2 * TILE);
-        ptx::tma_load_2d(smem + OFF_K, &tmK, kv_full, h * DH, b * p.Lk + j0);
-        ptx::tma_load_2d(smem + OFF_V, &tmV, kv_full, h * DH, b * p.Lk + j0);
+        ptx::tma_load_2d(smem + OFF_K, &tmK, kv_full, h * DH, k_row0 + j0);
+        ptx::tma_load_2d(smem + OFF_V, &tmV, kv_full, h * DH, k_row0 + j0);
         for (int n = 0; n < ntiles; ++n) {
           const int s = n & 1;
           if (n >= 2) ptx::mbar_wait(qdo_empty + s, ((n - 2) >> 1) & 1);
           ptx::mbar_expect_tx(qdo_full + s, 2 * TILE);
-          ptx::tma_load_2d(smem + OFF_Q + s * TILE, &tmQ, qdo_full + s, h * DH, b * p.Lq + (it0 + n) * BM);
-          ptx::tma_load_2d(smem + OFF_DO + s * TILE, &tmdO, qdo_full + s, h * DH, b * p.Lq + (it0 + n) * BM);
+          ptx::tma_load_2d(smem + OFF_Q + s * TILE, &tmQ, qdo_full + s, h * DH, q_row0 + (it0 + n) * BM);
+          ptx::tma_load_2d(smem + OFF_DO + s * TILE, &tmdO, qdo_full + s, h * DH, q_row0 + (it0 + n) * BM);
         }
       }
       __syncwarp();
@@ -182,7 +187,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (ptx::elect_one()) {
         for (int n = 0; n < ntiles; ++n) {
           ptx::mbar_wait(dqs_full, n & 1);              // all 16 warps have written dQ_n to the staging tile
-          const int row0 = b * p.Lq + (it0 + n) * BM;
+          const int row0 = q_row0 + (it0 + n) * BM;
           ptx::tma_reduce_add_2d(&tmDQ, smem + OFF_DQ, h * DH, row0);
           ptx::tma_reduce_add_2d(&tmDQ, smem + OFF_DQ + TILE, h * DH + 32, row0);
           ptx::tma_commit_group();
@@ -216,26 +221,25 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       kmask = __ballot_sync(0xffffffffu, msk);
     }
     const float c2 = p.c_log2;
-    const long long rowbase = ((long long)b * p.H + h) * p.Lq;
     const uint32_t sitekey = DROP ? attn_site_key(eff_seed(p.seed, p.seed_dev), p.site) : 0u;
     // per-row constants of a query tile are fetched one tile ahead (their global-load latency is off the critical path)
     float lse_nx = -INFINITY, dsum_nx = 0.f;
-    if (ntiles > 0 && it0 * BM + r < p.Lq) {
+    if (ntiles > 0 && it0 * BM + r < lq) {
       lse_nx = p.lse[rowbase + it0 * BM + r];
       dsum_nx = p.dsum[rowbase + it0 * BM + r];
     }
     for (int n = 0; n < ntiles; ++n) {
       const int iq0 = (it0 + n) * BM;
       const int i = iq0 + r;
-      const bool row_ok = i < p.Lq;
+      const bool row_ok = i < lq;
       // invalid rows: lse = -inf -> P = exp2(-inf) = 0
       const float lse2 = (!row_ok || lse_nx == -INFINITY) ? INFINITY : lse_nx * 1.4426950408889634f;
       const float dsum = row_ok ? dsum_nx : 0.f;
-      if (n + 1 < ntiles && i + BM < p.Lq) {
+      if (n + 1 < ntiles && i + BM < lq) {
         lse_nx = p.lse[rowbase + i + BM];
         dsum_nx = p.dsum[rowbase + i + BM];
       }
-      const int ii = row_ok ? i : p.Lq - 1;
+      const int ii = row_ok ? i : lq - 1;
       const uint32_t rowkey = DROP ? attn_row_key(sitekey, rowbase + ii) : 0u;
       uint32_t mw = kmask;
       if (p.causal && j0 + g * 32 + 31 > iq0) {
@@ -331,10 +335,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(dqs_full);
     }
     const int j = j0 + r;                              // TMEM lane = key row for dK / dV
-    const bool key_ok = j < p.Lk;
+    const bool key_ok = j < lk;
 #pragma unroll
     for (int part = 0; part < 2; ++part) {             // 0: dK (scaled), 1: dV; this warpgroup's 16 columns
-      bf16* drow = (part == 0 ? p.dk + ((long long)b * p.Lk + j) * p.lddk : p.dv + ((long long)b * p.Lk + j) * p.lddv) + h * DH + g * 16;
+      bf16* drow = (part == 0 ? p.dk + ((long long)k_row0 + j) * p.lddk : p.dv + ((long long)k_row0 + j) * p.lddv) + h * DH + g * 16;
       const float sc = part == 0 ? p.scale : 1.f;       // dV's operand Pd already carries keep/(1-p)
       uint32_t v[16];
       if (ntiles > 0) {                                  // uniform over the CTA
@@ -376,11 +380,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // D[b,h,i] = sum_c dO[i, h*64 + c] * O[i, h*64 + c]: 8 threads per (row, head), 16-byte loads
 __global__ void __launch_bounds__(256)
 attn_dsum_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ dout, long long lddo,
-                 float* __restrict__ dsum, int B, int H, int Lq) {
+                 float* __restrict__ dsum, long long rows, int H, int Lq, const int* __restrict__ cu_q, int B) {
   const long long t = blockIdx.x * 256ll + threadIdx.x;
   const long long grp = t >> 3;                       // (row, head)
   const int sub = (int)(t & 7);
-  const long long total = (long long)B * Lq * H;
+  const long long total = rows * H;
   float acc = 0.f;
   if (grp < total) {
     const long long row = grp / H;
@@ -402,8 +406,13 @@ attn_dsum_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restri
   if (grp < total && sub == 0) {
     const long long row = grp / H;
     const int hh = (int)(grp % H);
-    const long long bb = row / Lq, i = row % Lq;
-    dsum[(bb * H + hh) * Lq + i] = acc;
+    if (cu_q) {                                       // packed rows: head-major [H, cu_q[B]] (rows past cu_q[B] belong to nobody)
+      const long long tq = cu_q[B];
+      if (row < tq) dsum[hh * tq + row] = acc;
+    } else {
+      const long long bb = row / Lq, i = row % Lq;
+      dsum[(bb * H + hh) * Lq + i] = acc;
+    }
   }
 }
 
@@ -454,7 +463,7 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SMER_CHECK_ARG(a->dq_accum != nullptr, "smer_attn_bwd_tc: dq_accum (fp32 [B*Lq, H*64] workspace) is required");
   const long long dcols = (long long)a->H * DH;
-  const long long rq = (long long)a->B * a->Lq, rk = (long long)a->B * a->Lk;
+  const long long rq = a->cu_q ? a->q_rows : (long long)a->B * a->Lq, rk = a->cu_q ? a->k_rows : (long long)a->B * a->Lk;
   Params p;
   p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv; p.lddk = a->lddk; p.lddv = a->lddv;
   p.dq_acc = (float*)a->dq_accum;
@@ -465,6 +474,7 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
   p.thr2 = a->dropout_p > 0.f ? attn_dropout_threshold(a->dropout_p) * 0x10001u : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
+  p.cu_q = a->cu_q; p.cu_k = a->cu_k;
   static int attr_dev_mask = 0;
   int dev = 0;
   SMER_CUDA(cudaGetDevice(&dev));
@@ -483,7 +493,7 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
   {
     const long long threads = rq * a->H * 8;
     attn_dsum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const bf16*)a->o, a->ldo, (const bf16*)a->dout, a->lddo,
-                                                                        a->dsum, a->B, a->H, a->Lq);
+                                                                        a->dsum, rq, a->H, a->Lq, a->cu_q, a->B);
   }
   dim3 grid((a->Lk + BN - 1) / BN, a->H, a->B);
   if (p.thr2) attn_bwd2_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tk, tv, tdq, p);

@@ -57,6 +57,7 @@ struct Params {
   uint64_t seed, site;
   const unsigned long long* seed_dev;
   int npair, items;        // query-tile pairs per (b,h); npair * H * B work items
+  const int *cu_q, *cu_k;  // padding-free layout (smer_b200.h): per-sequence row ranges of the packed buffers, or NULL
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -78,6 +79,9 @@ struct Item {
   int ntk;                 // K / V tiles to load = max
   int klen;                // kv_len[b] clipped to Lk (before the causal bound)
   bool holes;              // the key mask is not a pure suffix: key_pad has to be read
+  int q_row0, k_row0;      // first row of sequence b in the Q / K,V buffers
+  int lq;                  // query rows of sequence b
+  long long stat0;         // index of (b, h, row 0) in lse (and the dropout row id)
 };
 
 __device__ __forceinline__ Item item_of(const Params& p, int item) {
@@ -89,11 +93,24 @@ __device__ __forceinline__ Item item_of(const Params& p, int item) {
   it.h = rem % p.H;
   it.b = rem / p.H;
   it.i0 = qp * 2 * BM;
-  const int kraw = p.kv_len ? p.kv_len[it.b] : p.Lk;
+  int kraw;
+  if (p.cu_q) {                                    // packed rows: every key of the sequence is visible
+    it.q_row0 = p.cu_q[it.b];
+    it.lq = p.cu_q[it.b + 1] - it.q_row0;
+    it.k_row0 = p.cu_k[it.b];
+    kraw = p.cu_k[it.b + 1] - it.k_row0;
+    it.stat0 = (long long)it.h * p.cu_q[p.B] + it.q_row0;
+  } else {
+    it.q_row0 = it.b * p.Lq;
+    it.lq = p.Lq;
+    it.k_row0 = it.b * p.Lk;
+    kraw = p.kv_len ? p.kv_len[it.b] : p.Lk;
+    it.stat0 = ((long long)it.b * p.H + it.h) * p.Lq;
+  }
   const int kl = min(abs(kraw), p.Lk);
   it.klen = kl;
   it.holes = p.pad != nullptr && (kraw < 0 || p.kv_len == nullptr);
-  int ke0 = it.i0 < p.Lq ? kl : 0, ke1 = it.i0 + BM < p.Lq ? kl : 0;
+  int ke0 = it.i0 < it.lq ? kl : 0, ke1 = it.i0 + BM < it.lq ? kl : 0;
   if (p.causal) { ke0 = min(ke0, it.i0 + BM); ke1 = min(ke1, it.i0 + 2 * BM); }
   it.kend0 = ke0; it.kend1 = ke1;
   it.nt0 = (ke0 + BN - 1) / BN; it.nt1 = (ke1 + BN - 1) / BN;
@@ -144,16 +161,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (it.ntk == 0) continue;
         if (qi > 0) ptx::mbar_wait(q_empty, (qi - 1) & 1);          // the previous item's S MMAs have read sQ
         ptx::mbar_expect_tx(q_full, it.nt1 > 0 ? 2 * TILE : TILE);
-        ptx::tma_load_2d(sQ, &tmQ, q_full, it.h * DH, it.b * p.Lq + it.i0);
-        if (it.nt1 > 0) ptx::tma_load_2d(sQ + TILE, &tmQ, q_full, it.h * DH, it.b * p.Lq + it.i0 + BM);
+        ptx::tma_load_2d(sQ, &tmQ, q_full, it.h * DH, it.q_row0 + it.i0);
+        if (it.nt1 > 0) ptx::tma_load_2d(sQ + TILE, &tmQ, q_full, it.h * DH, it.q_row0 + it.i0 + BM);
         for (int t = 0; t < it.ntk; ++t, ++g) {
           const uint32_t st = g % KS, ph = ((g / KS) - 1) & 1;
           if (g >= KS) ptx::mbar_wait(k_empty + st, ph);
           ptx::mbar_expect_tx(k_full + st, TILE);
-          ptx::tma_load_2d(sK + st * TILE, &tmK, k_full + st, it.h * DH, it.b * p.Lk + t * BN);
+          ptx::tma_load_2d(sK + st * TILE, &tmK, k_full + st, it.h * DH, it.k_row0 + t * BN);
           if (g >= KS) ptx::mbar_wait(v_empty + st, ph);
           ptx::mbar_expect_tx(v_full + st, TILE);
-          ptx::tma_load_2d(sV + st * TILE, &tmV, v_full + st, it.h * DH, it.b * p.Lk + t * BN);
+          ptx::tma_load_2d(sV + st * TILE, &tmV, v_full + st, it.h * DH, it.k_row0 + t * BN);
         }
         ++qi;
       }
@@ -247,9 +264,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int nt = c ? it.nt1 : it.nt0, kend = c ? it.kend1 : it.kend0;
       const int r0 = it.i0 + c * BM;
       const int i = r0 + r;
-      const bool row_ok = i < p.Lq;
-      const int ii = row_ok ? i : p.Lq - 1;
-      const long long rowid = ((long long)it.b * p.H + it.h) * p.Lq + ii;
+      const bool row_ok = i < it.lq;
+      const int ii = row_ok ? i : it.lq - 1;
+      const long long rowid = it.stat0 + ii;
       const uint32_t rowkey = DROP ? attn_row_key(sitekey, rowid) : 0u;
       // Masked keys: a pure suffix (the reference's padding, and every kv_len bound) is handled arithmetically below;
       // only a mask with holes needs the per-key bytes: its bitmap (bit j: key j masked) is built once per item by the
@@ -259,7 +276,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       bar_sync_qtile(c);                             // every thread of the query tile has left the previous item (O, bitmap, m/l)
       if (use_bitmap) {
         for (int j = (hf * 4 + quarter) * 32 + lane; j < nt * BN; j += 256) {
-          const bool msk = j >= kend || p.pad[(long long)it.b * p.Lk + j];
+          const bool msk = j >= kend || p.pad[(long long)it.b * p.Lk + j];      // (never with packed rows: no key_pad there)
           const uint32_t bal = __ballot_sync(0xffffffffu, msk);
           if (lane == 0) sts_u(a_mask + (j >> 5) * 4, bal);
         }
@@ -387,7 +404,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float inv = lt > 0.f ? p.inv_keep / lt : 0.f;      // dropout's 1/(1-p) applied once per row
         const float wa = fa * inv, wb = fb * inv;
         if (row_ok) {
-          bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
+          bf16* orow = p.o + ((long long)it.q_row0 + i) * p.ldo + it.h * DH + hf * 32;
 #pragma unroll
           for (int k = 0; k < 32; k += 8) {
             float f[8];
@@ -403,7 +420,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           if (p.lse && hf == 0) p.lse[rowid] = lt > 0.f ? (mm + log2f(lt)) * 0.6931471805599453f : -INFINITY;
         }
       } else if (row_ok) {                           // no visible key at all: zeros (uniform branch per query tile)
-        bf16* orow = p.o + ((long long)it.b * p.Lq + i) * p.ldo + it.h * DH + hf * 32;
+        bf16* orow = p.o + ((long long)it.q_row0 + i) * p.ldo + it.h * DH + hf * 32;
 #pragma unroll
         for (int k = 0; k < 32; k += 8) *reinterpret_cast<uint4*>(orow + k) = make_uint4(0u, 0u, 0u, 0u);
         if (p.lse && hf == 0) p.lse[rowid] = -INFINITY;
@@ -422,9 +439,10 @@ int smer_attn_fwd2_launch(const smer_attn_args* a, void* stream) {
   int rc;
   CUtensorMap tq, tk, tv;
   const long long dcols = (long long)a->H * DH;
-  if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, (long long)a->B * a->Lq, a->ldq, DH, BM))) return rc;
-  if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, (long long)a->B * a->Lk, a->ldk, DH, BN))) return rc;
-  if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, (long long)a->B * a->Lk, a->ldv, DH, BN))) return rc;
+  const long long rq = a->cu_q ? a->q_rows : (long long)a->B * a->Lq, rk = a->cu_q ? a->k_rows : (long long)a->B * a->Lk;
+  if ((rc = smer_make_tmap_bf16(&tq, a->q, dcols, rq, a->ldq, DH, BM))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, rk, a->ldk, DH, BN))) return rc;
+  if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, rk, a->ldv, DH, BN))) return rc;
   Params p;
   p.o = (bf16*)a->o; p.ldo = a->ldo; p.lse = a->lse; p.kv_len = a->kv_len; p.pad = a->key_pad;
   p.B = a->B; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk;
@@ -433,6 +451,7 @@ int smer_attn_fwd2_launch(const smer_attn_args* a, void* stream) {
   p.thr2 = a->dropout_p > 0.f ? attn_dropout_threshold(a->dropout_p) * 0x10001u : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
+  p.cu_q = a->cu_q; p.cu_k = a->cu_k;
   p.npair = (a->Lq + 2 * BM - 1) / (2 * BM);
   const long long items = (long long)p.npair * a->H * a->B;
   SMER_CHECK_ARG(items < (1ll << 31), "smer_attn_fwd_tc: too many work items");

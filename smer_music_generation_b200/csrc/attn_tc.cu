@@ -28,6 +28,11 @@ int check_common(const smer_attn_args* a, const char* who) {
   if (a->causal && a->Lq != a->Lk) { smer_set_error("%s: causal needs Lq == Lk", who); return SMER_ERR_UNSUPPORTED; }
   if (a->Lk > MASK_WORDS * 32) { smer_set_error("%s: Lk <= %d (key-mask bitmap in shared memory)", who, MASK_WORDS * 32); return SMER_ERR_UNSUPPORTED; }
   if (a->dropout_p > 0.45f) { smer_set_error("%s: dropout_p <= 0.45 (packed half-compare keep rule, common.cuh)", who); return SMER_ERR_UNSUPPORTED; }
+  if ((a->cu_q == nullptr) != (a->cu_k == nullptr)) { smer_set_error("%s: cu_q and cu_k come together", who); return SMER_ERR_ARG; }
+  if (a->cu_q && (a->kv_len || a->key_pad || a->q_rows <= 0 || a->k_rows <= 0)) {
+    smer_set_error("%s: packed rows (cu_q/cu_k) exclude kv_len / key_pad and need q_rows / k_rows", who);
+    return SMER_ERR_ARG;
+  }
   if (a->B <= 0 || a->H <= 0 || a->Lq <= 0 || a->Lk <= 0) { smer_set_error("%s: empty problem", who); return SMER_ERR_ARG; }
   return SMER_OK;
 }

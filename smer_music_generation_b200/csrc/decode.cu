@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(smer_decode_attn_a
   __shared__ float sm_m[DEC_GROUPS], sm_l[DEC_GROUPS];
   __shared__ float sm_acc[DEC_GROUPS][DH];
   int h = blockIdx.x, s = blockIdx.y, sp = blockIdx.z;
+  if (a.done && a.done[s]) return;                // a finished piece: nothing is appended, its K/V is not streamed
   int tid = threadIdx.x;
   int grp = tid / LPK, lig = tid % LPK;
   int npast = a.kv_len[s];                        // keys already in the cache
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(smer_decode_attn_a
 template <typename T, int DH>
 __global__ void decode_merge_kernel(smer_decode_attn_args a, int H) {
   int h = blockIdx.x, s = blockIdx.y, c = threadIdx.x;
+  if (a.done && a.done[s]) return;
   const float* w = a.workspace + ((long long)s * H + h) * a.splits * (DH + 2);
   float M = -INFINITY;
   for (int sp = 0; sp < a.splits; ++sp) M = fmaxf(M, w[sp * (DH + 2)]);
@@ -258,5 +260,43 @@ extern "C" int smer_embed_step(const int64_t* ids, const int* pos, const float* 
   else
     embed_step_kernel<bf16><<<grid, 256, 0, st>>>((const long long*)ids, pos, emb, pe, (bf16*)out, n_seq, d / 4, V, scale);
   SMER_CHECK_LAUNCH("smer_embed_step");
+  return SMER_OK;
+}
+
+// gather + embed in one launch: one CTA of d/4 threads per piece
+template <typename T>
+__global__ void decode_embed_kernel(const long long* __restrict__ tok_buf, const int* __restrict__ cur_len,
+                                    const int* __restrict__ fed_len, const int* __restrict__ done, int* __restrict__ pos,
+                                    const float* __restrict__ emb, const float* __restrict__ pe, T* __restrict__ out,
+                                    int max_len, int d4, int V, float scale) {
+  const int s = blockIdx.x;
+  if (done && done[s]) return;
+  int p = cur_len[s] - 1;
+  if (fed_len) p = min(p, fed_len[s]);
+  p = p < 0 ? 0 : (p >= max_len ? max_len - 1 : p);
+  long long id = tok_buf[(long long)s * max_len + p];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  if (threadIdx.x == 0) pos[s] = p;
+  for (int c4 = threadIdx.x; c4 < d4; c4 += blockDim.x) {
+    float e[4], q[4], o[4];
+    load4(emb + id * d4 * 4 + c4 * 4, e);
+    load4(pe + (long long)p * d4 * 4 + c4 * 4, q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = e[k] * scale + q[k];
+    store4(out + ((long long)s * d4 + c4) * 4, o);
+  }
+}
+
+extern "C" int smer_decode_embed(const int64_t* tok_buf, const int* cur_len, const int* fed_len, const int* done, int* pos,
+                                 const float* emb, const float* pe, void* out, int out_dtype, int n_seq, int max_len, int d,
+                                 int V, float scale, void* stream) {
+  SMER_CHECK_ARG(d % 4 == 0 && n_seq > 0, "smer_decode_embed: d must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = d / 4 < 128 ? (d / 4 + 31) / 32 * 32 : 128;
+  if (out_dtype == SMER_DT_F32)
+    decode_embed_kernel<float><<<n_seq, threads, 0, st>>>((const long long*)tok_buf, cur_len, fed_len, done, pos, emb, pe, (float*)out, max_len, d / 4, V, scale);
+  else
+    decode_embed_kernel<bf16><<<n_seq, threads, 0, st>>>((const long long*)tok_buf, cur_len, fed_len, done, pos, emb, pe, (bf16*)out, max_len, d / 4, V, scale);
+  SMER_CHECK_LAUNCH("smer_decode_embed");
   return SMER_OK;
 }

@@ -11,13 +11,14 @@ template <typename T>
 __global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb,
                                     const float* __restrict__ pe, T* __restrict__ out, long long n4,
                                     int L, int d4, int V, int pos0, float scale, uint32_t thr, float inv_keep,
-                                    uint64_t seed, uint64_t site, const unsigned long long* seed_dev) {
+                                    uint64_t seed, uint64_t site, const unsigned long long* seed_dev,
+                                    const int* __restrict__ pos = nullptr) {
   seed = eff_seed(seed, seed_dev);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     long long row = i / d4;
     int c4 = (int)(i - row * d4);
-    int l = (int)(row % L) + pos0;
+    int l = pos ? pos[row] : (int)(row % L) + pos0;
     long long id = ids[row];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
     float e[4], p[4], o[4];
@@ -85,6 +86,70 @@ extern "C" int smer_embed_pe_fwd(const int64_t* ids, const float* emb, const flo
   else
     embed_pe_fwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, emb, pe, (bf16*)out, n4, L, d / 4, V, pos0, scale, thr, inv_keep, seed, site, smer_seed_dev());
   SMER_CHECK_LAUNCH("smer_embed_pe_fwd");
+  return SMER_OK;
+}
+
+extern "C" int smer_embed_pe_packed(const int64_t* ids, const int* pos, const float* emb, const float* pe, void* out,
+                                    int out_dtype, long long rows, int d, int V, float scale, float dropout_p,
+                                    uint64_t seed, uint64_t site, void* stream) {
+  SMER_CHECK_ARG(d % 4 == 0 && rows > 0 && pos, "smer_embed_pe_packed: d must be a multiple of 4, pos required");
+  long long n4 = rows * (d / 4);
+  uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0u;
+  float inv_keep = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(n4, 256);
+  if (out_dtype == SMER_DT_F32)
+    embed_pe_fwd_kernel<float><<<grid, 256, 0, st>>>(ids, emb, pe, (float*)out, n4, 1, d / 4, V, 0, scale, thr, inv_keep, seed, site, smer_seed_dev(), pos);
+  else
+    embed_pe_fwd_kernel<bf16><<<grid, 256, 0, st>>>(ids, emb, pe, (bf16*)out, n4, 1, d / 4, V, 0, scale, thr, inv_keep, seed, site, smer_seed_dev(), pos);
+  SMER_CHECK_LAUNCH("smer_embed_pe_packed");
+  return SMER_OK;
+}
+
+__global__ void pack_rows_kernel(const int64_t* __restrict__ ids, const int* __restrict__ cu, int B, int L,
+                                 long long rows_alloc, int64_t* __restrict__ out_ids, int* __restrict__ out_pos) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < (long long)B * L) {
+    const int b = (int)(i / L), l = (int)(i - (long long)b * L);
+    const int base = cu[b], len = cu[b + 1] - base;
+    if (l < len) {
+      out_ids[base + l] = ids[i];
+      out_pos[base + l] = l;
+    }
+  }
+  // the tail [cu[B], rows_alloc): ghost rows that belong to no sequence
+  const long long tail0 = cu[B];
+  if (i < rows_alloc - tail0) {
+    out_ids[tail0 + i] = 0;
+    out_pos[tail0 + i] = 0;
+  }
+}
+
+extern "C" int smer_pack_rows(const int64_t* ids, const int* cu, int B, int L, long long rows_alloc, int64_t* out_ids,
+                              int* out_pos, void* stream) {
+  SMER_CHECK_ARG(B > 0 && L > 0 && rows_alloc > 0, "smer_pack_rows: bad shape");
+  long long n = (long long)B * L;
+  if (n < rows_alloc) n = rows_alloc;
+  pack_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, cu, B, L, rows_alloc, out_ids, out_pos);
+  SMER_CHECK_LAUNCH("smer_pack_rows");
+  return SMER_OK;
+}
+
+// rows [first_row[0], rows) of a row-major buffer := 0 (the ghost rows of a packed batch: no kernel of a sequence writes them)
+__global__ void zero_tail_rows_kernel(uint4* __restrict__ buf, long long row_vec, long long rows, const int* __restrict__ first_row) {
+  const long long r0 = first_row[0];
+  const long long n = (rows - r0) * row_vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row_vec, c = i - r * row_vec;
+    buf[(r0 + r) * row_vec + c] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+extern "C" int smer_zero_tail_rows(void* buf, long long row_bytes, long long rows, const int* first_row_dev, void* stream) {
+  SMER_CHECK_ARG(row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0 && first_row_dev,
+                 "smer_zero_tail_rows: rows must be contiguous multiples of 16 bytes");
+  zero_tail_rows_kernel<<<64, 256, 0, (cudaStream_t)stream>>>((uint4*)buf, row_bytes / 16, rows, first_row_dev);
+  SMER_CHECK_LAUNCH("smer_zero_tail_rows");
   return SMER_OK;
 }
 

@@ -335,6 +335,7 @@ class InfillDecoder:
         a.n_seq, a.H, a.dh, a.cache_len, a.splits = self.n, m.nhead, m.d_model // m.nhead, cache_len, self.splits
         a.dtype = K.dt(q)
         a.scale = 1.0 / math.sqrt(m.d_model // m.nhead)
+        a.done = self.done.data_ptr()                 # finished pieces stop streaming their K/V
         K.check(K.lib().smer_decode_attn(C.byref(a), K.stream()), "decode_attn")
         if prof is not None:
             e1 = torch.cuda.Event(enable_timing=True)
@@ -347,13 +348,12 @@ class InfillDecoder:
         d = m.d_model
         n, L, S = self.n, self.max_len, self.S
         lib = K.lib()
-        K.check(lib.smer_decode_gather(self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.fed_len.data_ptr(),
-                                       self.ids.data_ptr(), self.pos.data_ptr(), n, L, K.stream()), "decode_gather")
-        K.check(lib.smer_embed_step(self.ids.data_ptr(), self.pos.data_ptr(), m.embedding.weight.data_ptr(),
-                                    m.pos_enc.pe.data_ptr(), b["x"].data_ptr(), K.dt(b["x"]), n, d, m.vocab_size,
-                                    math.sqrt(d), K.stream()), "embed_step")
+        K.check(lib.smer_decode_embed(self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.fed_len.data_ptr(),
+                                      self.done.data_ptr(), self.pos.data_ptr(), m.embedding.weight.data_ptr(),
+                                      m.pos_enc.pe.data_ptr(), b["x"].data_ptr(), K.dt(b["x"]), n, L, d, m.vocab_size,
+                                      math.sqrt(d), K.stream()), "decode_embed")
         x = b["x"]
-        launches = 2
+        launches = 1
         for i, lp in enumerate(self.layer_p):
             sa, ca = lp.sa, lp.ca
             qkv = b["qkv"]

@@ -361,10 +361,60 @@ class ScoreTransformer(nn.Module):
 # ----------------------------------------------------------------------------------------
 # one forward(/backward) execution
 # ----------------------------------------------------------------------------------------
+class PackedBatch:
+    """A batch without padding rows: the tokens of all sequences back to back, token-major, with int32
+    prefix sums `cu_*` (B+1 entries, device) marking each sequence's rows.  The reference's collate functions pad every
+    sequence of a bucket to the longest one (dataset.py:802-925); `pack()` removes those pads on the device from the padded
+    batch and the per-sequence lengths, which the collate step knows on the host.  Row counts are rounded up to `align`
+    (the extra "ghost" rows belong to no sequence, carry token id 0 and contribute nothing)."""
+
+    def __init__(self, src_ids, tgt_in, tgt_out, pos_s, pos_t, cu_s, cu_t, n_s, n_t, max_s, max_t, B):
+        self.src_ids, self.tgt_in, self.tgt_out = src_ids, tgt_in, tgt_out
+        self.pos_s, self.pos_t, self.cu_s, self.cu_t = pos_s, pos_t, cu_s, cu_t
+        self.n_s, self.n_t, self.max_s, self.max_t, self.B = n_s, n_t, max_s, max_t, B
+        self.rows_s, self.rows_t = src_ids.numel(), tgt_in.numel()
+
+    @staticmethod
+    def pack(src, tgt_in, tgt_out, src_lens, tgt_lens, align: int = 128, rows_s: int = 0, rows_t: int = 0, out=None):
+        """src / tgt_in / tgt_out: padded (B, S) / (B, T) int64 DEVICE tensors; src_lens / tgt_lens: HOST sequences of
+        the un-padded lengths.  rows_s / rows_t force the packed row counts (fixed shapes for a captured step);
+        out: a PackedBatch whose buffers are refilled in place."""
+        dev = src.device
+        B = src.shape[0]
+        ls = [int(x) for x in src_lens]
+        lt = [int(x) for x in tgt_lens]
+        n_s, n_t = sum(ls), sum(lt)
+        up = lambda n: (n + align - 1) // align * align
+        rows_s, rows_t = max(rows_s, up(n_s)), max(rows_t, up(n_t))
+        cu = torch.zeros(2, B + 1, dtype=torch.int32)
+        cu[0, 1:] = torch.tensor(ls, dtype=torch.int32).cumsum(0)
+        cu[1, 1:] = torch.tensor(lt, dtype=torch.int32).cumsum(0)
+        if out is None:
+            cu_d = cu.to(dev)
+            mk = lambda n, dt: torch.empty(n, dtype=dt, device=dev)
+            out = PackedBatch(mk(rows_s, torch.int64), mk(rows_t, torch.int64), mk(rows_t, torch.int64), mk(rows_s, torch.int32),
+                              mk(rows_t, torch.int32), cu_d[0], cu_d[1], n_s, n_t, max(ls), max(lt), B)
+            out._cu2 = cu_d
+        else:
+            if out.rows_s < up(n_s) or out.rows_t < up(n_t) or out.B != B:
+                raise RuntimeError("PackedBatch.pack: the batch does not fit the preallocated rows")
+            out._cu2.copy_(cu, non_blocking=True)
+            out.n_s, out.n_t, out.max_s, out.max_t = n_s, n_t, max(ls), max(lt)
+        ops.pack_rows(src, out.cu_s, out.rows_s, out.src_ids, out.pos_s)
+        ops.pack_rows(tgt_in, out.cu_t, out.rows_t, out.tgt_in, out.pos_t)
+        ops.pack_rows(tgt_out, out.cu_t, out.rows_t, out.tgt_out, out.pos_t)
+        return out
+
+
 class _Run:
     def __init__(self, model: ScoreTransformer, src, tgt, src_pad, tgt_pad, mem_pad, causal, add_mask, training,
-                 seed, want_w):
+                 seed, want_w, packed: Optional[PackedBatch] = None):
         self.m = model
+        self.pk = packed
+        if packed is not None:
+            # packed rows: (B, S, T) = (sequences, longest source, longest target); pads do not exist
+            src, tgt = packed.src_ids.view(1, -1), packed.tgt_in.view(1, -1)
+            src_pad = tgt_pad = mem_pad = None
         self.src, self.tgt = src, tgt
         self.src_pad, self.tgt_pad, self.mem_pad = src_pad, tgt_pad, mem_pad
         self.causal, self.add_mask = causal, add_mask
@@ -372,6 +422,11 @@ class _Run:
         self.dt = model.compute_dtype
         self.B, self.S = src.shape
         self.T = tgt.shape[1]
+        self.rows_s, self.rows_t = self.B * self.S, self.B * self.T
+        if packed is not None:
+            if model.compute_dtype != torch.bfloat16 or want_w or not causal or add_mask is not None:
+                raise RuntimeError("packed batches run on the bf16 tcgen05 path with the nopeek mask and without attention weights")
+            self.B, self.S, self.T = packed.B, packed.max_s, packed.max_t
         self.d, self.H, self.ff = model.d_model, model.nhead, model.dim_feedforward
         self.dh = self.d // self.H
         self.pd = model.pos_dropout if training else 0.0
@@ -417,61 +472,81 @@ class _Run:
                           dbias=grads[bias_name] if bias_name is not None else None)   # bias grad of the branch's Linear
         return dz, (dbr if dbr is not None else dz)
 
-    def _attn_fwd(self, ap: _AttnP, xq, xkv, Lq, Lk, causal, key_pad, kv_len, add_mask, site_p, key, save, weights_out=None):
+    def _attn_fwd(self, ap: _AttnP, xq, xkv, Lq, Lk, causal, key_pad, kv_len, add_mask, site_p, key, save, weights_out=None,
+                  side="s"):
         B, d, H, dh = self.B, self.d, self.H, self.dh
         self_attn = xkv is None
+        rq = xq.shape[0]
+        rk = rq if self_attn else xkv.shape[0]
+        pk = self.pk
+        cu_q = cu_k = None
+        if pk is not None:
+            cu_q = pk.cu_s if side == "s" else pk.cu_t
+            cu_k = cu_q if self_attn else pk.cu_s
         if self_attn:
-            qkv = self.new(B * Lq, 3 * d)
+            qkv = self.new(rq, 3 * d)
             ops.gemm_nt(xq, ap.w, qkv, bias=ap.b)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
             kvbuf = None
         else:
-            qkv = self.new(B * Lq, d)
+            qkv = self.new(rq, d)
             ops.gemm_nt(xq, ap.w[:d], qkv, bias=ap.b[:d])
-            kvbuf = self.new(B * Lk, 2 * d)
+            kvbuf = self.new(rk, 2 * d)
             ops.gemm_nt(xkv, ap.w[d:3 * d], kvbuf, bias=ap.b[d:])
             q, k, v = qkv, kvbuf[:, :d], kvbuf[:, d:]
-        o = self.new(B * Lq, d)
-        lse = torch.empty(B, H, Lq, dtype=torch.float32, device=self.dev)
+        o = self.new(rq, d)
+        if pk is not None:
+            ops.zero_tail_rows(o, cu_q)           # ghost rows belong to no sequence: the kernels never write them
+        lse = torch.empty(H * rq if pk is not None else B * H * Lq, dtype=torch.float32, device=self.dev)
         a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=key_pad, kv_len=kv_len,
-                          add_mask=add_mask, dropout_p=self.td, seed=self.seed, site=site_p)
+                          add_mask=add_mask, dropout_p=self.td, seed=self.seed, site=site_p, cu_q=cu_q, cu_k=cu_k)
         ops.attn_fwd(a)
         if weights_out is not None:
             ops.attn_weights(a, weights_out)
-        proj = self.new(B * Lq, d)
+        proj = self.new(rq, d)
         ops.gemm_nt(o, ap.wo, proj, bias=ap.bo)
         if save:
             self.tape[key] = (qkv, kvbuf, o, lse)
         return proj
 
     def _attn_bwd(self, ap: _AttnP, dproj, xq, xkv, Lq, Lk, causal, key_pad, kv_len, add_mask, site_p, key, grads,
-                  resid_q, dmem=None):
+                  resid_q, dmem=None, side="s"):
         """Returns grad wrt xq (residual `resid_q` folded in).  For cross-attention the K/V-side
         input gradient is accumulated into `dmem`."""
         B, d, H, dh = self.B, self.d, self.H, self.dh
         qkv, kvbuf, o, lse = self.tape.pop(key)
         n = ap.name
+        rq = dproj.shape[0]
+        pk = self.pk
+        cu_q = cu_k = None
         ops.gemm_dw(dproj, o, grads[n + "out_proj.weight"])         # out_proj.bias: summed inside layernorm_bwd
-        do = self.new(B * Lq, d)
+        do = self.new(rq, d)
         ops.gemm_dx(dproj, ap.wo, do)
-        dsum = torch.empty(B, H, Lq, dtype=torch.float32, device=self.dev)
+        dsum = torch.empty(H * rq if pk is not None else B * H * Lq, dtype=torch.float32, device=self.dev)
         self_attn = kvbuf is None
+        if pk is not None:
+            cu_q = pk.cu_s if side == "s" else pk.cu_t
+            cu_k = cu_q if self_attn else pk.cu_s
         if self_attn:
-            dqkv = self.new(B * Lq, 3 * d)
+            dqkv = self.new(rq, 3 * d)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
             dq, dk, dv = dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]
+            if pk is not None:
+                ops.zero_tail_rows(dqkv, cu_q)    # ghost rows: the backward kernel writes dK / dV rows of real keys only
         else:
-            dqkv = self.new(B * Lq, d)
-            dkv = self.new(B * Lk, 2 * d)
+            dqkv = self.new(rq, d)
+            dkv = self.new(kvbuf.shape[0], 2 * d)
             q, k, v = qkv, kvbuf[:, :d], kvbuf[:, d:]
             dq, dk, dv = dqkv, dkv[:, :d], dkv[:, d:]
+            if pk is not None:
+                ops.zero_tail_rows(dkv, cu_k)
         gw, gb = grads[n + "in_proj_weight"], grads[n + "in_proj_bias"]
         # in_proj_bias gradient = column sums of dq | dk | dv, accumulated by the attention backward kernels
         a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=key_pad, kv_len=kv_len,
                           add_mask=add_mask, dropout_p=self.td, seed=self.seed, site=site_p, dout=do, dq=dq, dk=dk,
-                          dv=dv, dsum=dsum, dbq=gb[:d], dbk=gb[d:2 * d], dbv=gb[2 * d:])
+                          dv=dv, dsum=dsum, dbq=gb[:d], dbk=gb[d:2 * d], dbv=gb[2 * d:], cu_q=cu_q, cu_k=cu_k)
         ops.attn_bwd(a)
-        dx = self.new(B * Lq, d)
+        dx = self.new(rq, d)
         if self_attn:
             ops.gemm_dw(dqkv, xq, gw)
             ops.gemm_dx(dqkv, ap.w, dx, resid=resid_q)
@@ -516,8 +591,11 @@ class _Run:
         pe = m.pos_enc.pe.view(-1, d)
         emb = m.embedding.weight.detach()
         scale = math.sqrt(d)
-        x = self.new(B * S, d)
-        ops.embed_pe(self.src, emb, pe, x, scale, 0, self.pd, self.seed, _SITE_EMB_SRC)
+        x = self.new(self.rows_s, d)
+        if self.pk is not None:
+            ops.embed_pe_packed(self.pk.src_ids, self.pk.pos_s, emb, pe, x, scale, self.pd, self.seed, _SITE_EMB_SRC)
+        else:
+            ops.embed_pe(self.src, emb, pe, x, scale, 0, self.pd, self.seed, _SITE_EMB_SRC)
         enc = m.transformer.encoder
         self.enc_p = [m._layer_p(l, f"transformer.encoder.layers.{i}.") for i, l in enumerate(enc.layers)]
         for i, lp in enumerate(self.enc_p):
@@ -543,8 +621,11 @@ class _Run:
         pe = m.pos_enc.pe.view(-1, d)
         emb = m.embedding.weight.detach()
         scale = math.sqrt(d)
-        y = self.new(B * T, d)
-        ops.embed_pe(self.tgt, emb, pe, y, scale, 0, self.pd, self.seed, _SITE_EMB_TGT)
+        y = self.new(self.rows_t, d)
+        if self.pk is not None:
+            ops.embed_pe_packed(self.pk.tgt_in, self.pk.pos_t, emb, pe, y, scale, self.pd, self.seed, _SITE_EMB_TGT)
+        else:
+            ops.embed_pe(self.tgt, emb, pe, y, scale, 0, self.pd, self.seed, _SITE_EMB_TGT)
         dec = m.transformer.decoder
         self.dec_p = [m._layer_p(l, f"transformer.decoder.layers.{i}.") for i, l in enumerate(dec.layers)]
         if self.want_w:
@@ -553,13 +634,13 @@ class _Run:
             if save:
                 self.tape[f"d{i}.y"] = y
             a = self._attn_fwd(lp.sa, y, None, T, T, self.causal, self.tgt_pad, self.tgt_len, self.add_mask,
-                               _site(_KIND_DEC, i, _SUB_ATTN_P), f"d{i}.sa", save)
+                               _site(_KIND_DEC, i, _SUB_ATTN_P), f"d{i}.sa", save, side="t")
             y1 = self._ln_fwd(a, y, lp.ln[0], _site(_KIND_DEC, i, _SUB_DROP1), f"d{i}.ln1", save)
             if save:
                 self.tape[f"d{i}.y1"] = y1
             c = self._attn_fwd(lp.ca, y1, mem, T, S, False, self.mem_pad, self.mem_len, None,
                                _site(_KIND_DEC, i, _SUB_XATTN_P), f"d{i}.ca", save,
-                               weights_out=self.weights[i] if self.want_w else None)
+                               weights_out=self.weights[i] if self.want_w else None, side="t")
             y2 = self._ln_fwd(c, y1, lp.ln[1], _site(_KIND_DEC, i, _SUB_DROP2), f"d{i}.ln2", save)
             if save:
                 self.tape[f"d{i}.y2"] = y2
@@ -571,7 +652,7 @@ class _Run:
             self.tape["yo"] = yo
         wfc, bfc = m._fc_p()
         self.fc_p = (wfc, bfc)
-        logits = torch.empty(B * T, wfc.shape[0], dtype=torch.float32, device=self.dev)
+        logits = torch.empty(self.rows_t, wfc.shape[0], dtype=torch.float32, device=self.dev)
         ops.gemm_nt(yo, wfc, logits, bias=bfc)
         return logits
 
@@ -584,7 +665,7 @@ class _Run:
         yo = self.tape.pop("yo")
         ops.colsum(dlogits, grads["fc.bias"])
         ops.gemm_dw(dlogits, yo, grads["fc.weight"])
-        dyo = self.new(B * T, d)
+        dyo = self.new(self.rows_t, d)
         ops.gemm_dx(dlogits, wfc, dyo)
         if hook:
             hook("fc.")
@@ -592,7 +673,7 @@ class _Run:
         if hook:
             hook("transformer.decoder.norm.")
         mem = self.tape.pop("mem")
-        dmem = torch.zeros(B * S, d, dtype=self.dt, device=self.dev)
+        dmem = torch.zeros(self.rows_s, d, dtype=self.dt, device=self.dev)
         for i in reversed(range(len(self.dec_p))):
             lp = self.dec_p[i]
             n = lp.name
@@ -602,11 +683,11 @@ class _Run:
             dz2, dc = self._ln_bwd(dy2, lp.ln[1], _site(_KIND_DEC, i, _SUB_DROP2), f"d{i}.ln2", grads, n + "norm2.",
                                    bias_name=n + "multihead_attn.out_proj.bias")
             dy1 = self._attn_bwd(lp.ca, dc, self.tape.pop(f"d{i}.y1"), mem, T, S, False, self.mem_pad, self.mem_len,
-                                 None, _site(_KIND_DEC, i, _SUB_XATTN_P), f"d{i}.ca", grads, dz2, dmem)
+                                 None, _site(_KIND_DEC, i, _SUB_XATTN_P), f"d{i}.ca", grads, dz2, dmem, side="t")
             dz1, da = self._ln_bwd(dy1, lp.ln[0], _site(_KIND_DEC, i, _SUB_DROP1), f"d{i}.ln1", grads, n + "norm1.",
                                    bias_name=n + "self_attn.out_proj.bias")
             dy = self._attn_bwd(lp.sa, da, self.tape.pop(f"d{i}.y"), None, T, T, self.causal, self.tgt_pad,
-                                self.tgt_len, self.add_mask, _site(_KIND_DEC, i, _SUB_ATTN_P), f"d{i}.sa", grads, dz1)
+                                self.tgt_len, self.add_mask, _site(_KIND_DEC, i, _SUB_ATTN_P), f"d{i}.sa", grads, dz1, side="t")
             if hook:
                 hook(n)
         emb_scale = math.sqrt(d)

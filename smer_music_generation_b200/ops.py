@@ -61,6 +61,27 @@ def embed_pe(ids, emb, pe, out, scale, pos0=0, dropout_p=0.0, seed=0, site=0):
                                           dropout_p, seed, site, K.stream()), "embed_pe_fwd")
 
 
+def embed_pe_packed(ids, pos, emb, pe, out, scale, dropout_p=0.0, seed=0, site=0):
+    with _Timed("embed", float(ids.numel() * emb.shape[1] * (4 + out.element_size())), 1):
+        V, d = emb.shape
+        K.check(K.lib().smer_embed_pe_packed(_p(ids), _p(pos), _p(emb), _p(pe), _p(out), K.dt(out), ids.numel(), d, V, scale,
+                                             dropout_p, seed, site, K.stream()), "embed_pe_packed")
+
+
+def pack_rows(ids_padded, cu, rows_alloc, out_ids, out_pos):
+    with _Timed("misc", 0.0, 1):
+        B, L = ids_padded.shape
+        K.check(K.lib().smer_pack_rows(_p(ids_padded), _p(cu), B, L, rows_alloc, _p(out_ids), _p(out_pos), K.stream()), "pack_rows")
+
+
+def zero_tail_rows(buf, cu):
+    """Zeroes the rows of the contiguous 2-D `buf` from cu[-1] (device value) on: the ghost rows of a packed batch."""
+    with _Timed("misc", 0.0, 1):
+        assert buf.is_contiguous()
+        K.check(K.lib().smer_zero_tail_rows(_p(buf), buf.shape[1] * buf.element_size(), buf.shape[0], cu[-1:].data_ptr(),
+                                            K.stream()), "zero_tail_rows")
+
+
 def embed_bwd(ids, dout, demb, scale, dropout_p=0.0, seed=0, site=0):
     with _Timed("embed_bwd", float(ids.numel() * demb.shape[1] * (4 + dout.element_size())), 1):
         B, L = ids.shape
@@ -175,7 +196,7 @@ def colsum(x, out):
 
 def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0, key_pad=None, kv_len=None,
               add_mask=None, dropout_p=0.0, seed=0, site=0, dout=None, dq=None, dk=None, dv=None, dsum=None,
-              dbq=None, dbk=None, dbv=None, dq_accum=None):
+              dbq=None, dbk=None, dbv=None, dq_accum=None, cu_q=None, cu_k=None):
     """dbq/dbk/dbv (fp32 [H*dh], backward): += column sums of dq/dk/dv = the in-projection's bias gradient."""
     a = K.AttnArgs()
     a.dbq, a.dbk, a.dbv = _p(dbq), _p(dbk), _p(dbv)
@@ -198,6 +219,10 @@ def attn_args(q, k, v, o, B, H, Lq, Lk, dh, *, lse=None, causal=False, q_pos0=0,
     a.dropout_p, a.seed, a.site = dropout_p, seed, site
     a.dq_accum = _p(dq_accum)
     a._keep = dq_accum
+    # padding-free layout: per-sequence row ranges of the packed q / k,v buffers (B, Lq, Lk then mean: sequences,
+    # longest query sequence, longest key sequence)
+    a.cu_q, a.cu_k = _p(cu_q), _p(cu_k)
+    a.q_rows, a.k_rows = (q.shape[0], k.shape[0]) if cu_q is not None else (0, 0)
     return a
 
 
@@ -215,6 +240,8 @@ def _attn_flops(a):
 
 
 def attn_fwd(a):
+    if a.cu_q and not _attn_tc_ok(a):
+        raise RuntimeError("packed-row attention needs the tcgen05 kernels (bf16, head dim 64, no additive mask)")
     with _Timed("attn_fwd", _attn_flops(a)):
         if _attn_tc_ok(a) and ATTN_TC_FWD:
             K.check(K.lib().smer_attn_fwd_tc(C.byref(a), K.stream()), "attn_fwd_tc")
@@ -224,9 +251,12 @@ def attn_fwd(a):
 
 def attn_bwd(a):
     tc = _attn_tc_ok(a) and ATTN_TC_BWD
+    if a.cu_q and not tc:
+        raise RuntimeError("packed-row attention needs the tcgen05 kernels (bf16, head dim 64, no additive mask)")
     if tc and not a.dq_accum:
         # fp32 accumulation buffer of the fused backward (dQ partial sums of the key-tile CTAs)
-        a._keep = torch.empty(a.B * a.Lq, a.H * a.dh, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        rows = a.q_rows if a.cu_q else a.B * a.Lq
+        a._keep = torch.empty(rows, a.H * a.dh, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
         a.dq_accum = a._keep.data_ptr()
     with _Timed("attn_bwd", 2.0 * _attn_flops(a), 3 if tc else 3):      # tc: D = rowsum(dO o O), fused dQ/dK/dV, dQ convert
         if tc:

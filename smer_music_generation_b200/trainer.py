@@ -22,7 +22,7 @@ import torch
 from . import _capi as K
 from . import ops
 from .loss import CATEGORIES, CONTROL_NAMES, loss_tables
-from .model import GradArena, ScoreTransformer, _Run
+from .model import GradArena, PackedBatch, ScoreTransformer, _Run
 
 
 _SEED_OWNER = [None]        # id() of the TrainEngine whose step counter the library's seed pointer refers to
@@ -168,12 +168,17 @@ class TrainEngine:
         self._step_impl(src, tgt_in, tgt_out, src_pad, tgt_pad, seed, update, None)
         return self.sums
 
-    def _step_impl(self, src, tgt_in, tgt_out, src_pad, tgt_pad, seed, update, step_dev):
+    def _step_impl(self, src, tgt_in, tgt_out, src_pad, tgt_pad, seed, update, step_dev, packed: Optional[PackedBatch] = None):
         m = self.model
-        B, S = src.shape
-        T = tgt_in.shape[1]
-        pad_s = None if src_pad is None else src_pad.to(torch.uint8)
-        pad_t = None if tgt_pad is None else tgt_pad.to(torch.uint8)
+        if packed is not None:
+            pad_s = pad_t = None
+            rows_t = packed.rows_t
+            tgt_out = packed.tgt_out
+        else:
+            B, S = src.shape
+            rows_t = B * tgt_in.shape[1]
+            pad_s = None if src_pad is None else src_pad.to(torch.uint8)
+            pad_t = None if tgt_pad is None else tgt_pad.to(torch.uint8)
         V, vp = m.vocab_size, m.vpad
         tg = tgt_out.reshape(-1)
         dp = self.world > 1
@@ -183,11 +188,11 @@ class TrainEngine:
             import torch.distributed as dist
             ops.xent_denominator(tg, self.C, self.denom, V)
             self._on_comm(lambda: dist.all_reduce(self.denom, op=dist.ReduceOp.SUM, group=self.pg))
-        run = _Run(m, src, tgt_in, pad_s, pad_t, pad_s, True, None, True, seed, False)
-        logits = run.forward(save=True)                              # (B*T, vpad) fp32
-        lse = torch.empty(B * T, dtype=torch.float32, device=self.dev)
+        run = _Run(m, src, tgt_in, pad_s, pad_t, pad_s, True, None, True, seed, False, packed=packed)
+        logits = run.forward(save=True)                              # (rows, vpad) fp32
+        lse = torch.empty(rows_t, dtype=torch.float32, device=self.dev)
         ops.xent_fwd(logits, tg, self.W, self.C, self.cat, self.ncat, lse, self.sums, V)
-        dl = torch.empty(B * T, vp, dtype=m.compute_dtype, device=self.dev)
+        dl = torch.empty(rows_t, vp, dtype=m.compute_dtype, device=self.dev)
         if dp:
             if self.comm_stream is not None:
                 torch.cuda.current_stream().wait_event(self._denom_ready)
@@ -210,6 +215,80 @@ class TrainEngine:
             a = self.arena
             ops.adam_step(a.flat, self.grads.flat, a.m, a.v, a.shadow, self.step_count, self.lr, self.betas[0],
                           self.betas[1], self.eps, 1.0, step_dev=step_dev)
+
+    # ---- padding-free batches ---------------------------------------------
+    def step_packed(self, packed: PackedBatch, update: bool = True):
+        """One training step on a batch without padding rows (model.PackedBatch).  Same arithmetic on the same tokens as
+        step() on the padded batch: pad positions never reach the loss (ignore_index 0) nor any attention (masked keys)."""
+        if not self.model.training:
+            raise RuntimeError("TrainEngine.step needs model.train()")
+        self.step_count += 1
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self.step_count * 0xD1342543DE82EF95
+                + (0 if self.pg is None else 7919 * torch.distributed.get_rank(self.pg))) & 0xFFFFFFFFFFFFFFFF
+        self._step_impl(None, None, None, None, None, seed, update, None, packed=packed)
+        return self.sums
+
+    def capture_packed(self, B: int, rows_s: int, rows_t: int, max_s: int, max_t: int):
+        """CUDA graph of one packed step for fixed row counts: a replay serves every batch of B sequences whose packed
+        rows fit (rows are rounded up; attention grids are sized for sequences up to max_s / max_t)."""
+        dev = self.dev
+        pad_src = torch.zeros(B, max_s, dtype=torch.int64, device=dev)
+        pad_tgt = torch.zeros(B, max_t, dtype=torch.int64, device=dev)
+        pad_src[:, :1] = 3
+        pad_tgt[:, :1] = 3
+        pk = PackedBatch.pack(pad_src, pad_tgt, pad_tgt, [1] * B, [1] * B, rows_s=rows_s, rows_t=rows_t)
+        pk.max_s, pk.max_t = max_s, max_t
+        self._g_pk = pk
+        self._g_pad = dict(src=torch.zeros(B, max_s, dtype=torch.int64, device=dev),
+                           tgt_in=torch.zeros(B, max_t, dtype=torch.int64, device=dev),
+                           tgt_out=torch.zeros(B, max_t, dtype=torch.int64, device=dev))
+        self._ctr = torch.full((1,), self.step_count, dtype=torch.int64, device=dev)
+        K.check(K.lib().smer_set_seed_device_ptr(self._ctr.data_ptr()), "set_seed_device_ptr")
+        _SEED_OWNER[0] = id(self)
+        self._seed_base = (torch.initial_seed() * 0x9E3779B97F4A7C15
+                           + (0 if self.pg is None else 7919 * torch.distributed.get_rank(self.pg))) & 0xFFFFFFFFFFFFFFFF
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step_impl(None, None, None, None, None, self._seed_base, False, self._ctr, packed=pk)
+            scratch = [torch.zeros(1024, dtype=torch.float32, device=dev) for _ in range(4)]
+            sh = torch.zeros(1024, dtype=torch.bfloat16, device=dev) if self.arena.shadow is not None else None
+            one = torch.ones(1, dtype=torch.int64, device=dev)
+            ops.adam_step(scratch[0], scratch[1], scratch[2], scratch[3], sh, 1, self.lr, self.betas[0], self.betas[1],
+                          self.eps, 1.0, step_dev=one)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._ctr.add_(1)
+            # the on-GPU collate (padded ids -> packed rows) is part of the captured step
+            ops.pack_rows(self._g_pad["src"], pk.cu_s, pk.rows_s, pk.src_ids, pk.pos_s)
+            ops.pack_rows(self._g_pad["tgt_in"], pk.cu_t, pk.rows_t, pk.tgt_in, pk.pos_t)
+            ops.pack_rows(self._g_pad["tgt_out"], pk.cu_t, pk.rows_t, pk.tgt_out, pk.pos_t)
+            self._step_impl(None, None, None, None, None, self._seed_base, True, self._ctr, packed=pk)
+        return self
+
+    def step_graph_packed(self, src, tgt_in, tgt_out, src_lens, tgt_lens):
+        """Padded batch (host pinned or device tensors, as the reference's DataLoader yields them) + the HOST lengths of its
+        sequences -> copies them in, packs them on the device and replays the captured packed step."""
+        pk, gp = self._g_pk, self._g_pad
+        B = src.shape[0]
+        ls = torch.as_tensor(src_lens, dtype=torch.int32)
+        lt = torch.as_tensor(tgt_lens, dtype=torch.int32)
+        n_s, n_t = int(ls.sum()), int(lt.sum())
+        if n_s > pk.rows_s or n_t > pk.rows_t or int(ls.max()) > pk.max_s or int(lt.max()) > pk.max_t or B != pk.B:
+            raise RuntimeError("step_graph_packed: the batch does not fit the captured shape")
+        cu = torch.zeros(2, B + 1, dtype=torch.int32)
+        cu[0, 1:] = ls.cumsum(0)
+        cu[1, 1:] = lt.cumsum(0)
+        pk._cu2.copy_(cu.pin_memory() if src.is_pinned() else cu, non_blocking=True)
+        gp["src"][:, : src.shape[1]].copy_(src, non_blocking=True)
+        gp["tgt_in"][:, : tgt_in.shape[1]].copy_(tgt_in, non_blocking=True)
+        gp["tgt_out"][:, : tgt_out.shape[1]].copy_(tgt_out, non_blocking=True)
+        pk.n_s, pk.n_t = n_s, n_t
+        self.step_count += 1
+        self._graph.replay()
+        return self.sums
 
     def _on_comm(self, fn, record=True):
         """Runs a collective on the communication stream after everything enqueued so far on the current stream

@@ -235,3 +235,64 @@ def test_two_gpu_engine_grads_equal_single_gpu_on_concatenated_batch(oracle):
         ref = g.cpu()
         err = (grads2[n] - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
         assert err < 1e-4, (n, err)
+
+
+def test_packed_rows_match_padded_batch_and_oracle(oracle):
+    """Padding-free layout: a ragged batch run as packed rows + cu_seqlens gives the loss sums and
+    gradients of the padded run of the same batch (same kernels, other tile boundaries: bf16 tolerance) and of the
+    oracle; tokens are the same non-pad tokens.  Also through the captured step with the on-GPU collate."""
+    from smer_music_generation_b200 import ScoreTransformer
+    from smer_music_generation_b200.model import PackedBatch
+    from smer_music_generation_b200.trainer import TrainEngine
+    O = oracle
+    cfg = dict(d=128, h=2, le=2, ld=2, ff=256, maxlen=512)
+    sd = O.random_state_dict(cfg["d"], cfg["h"], cfg["le"], cfg["ld"], cfg["ff"], cfg["maxlen"], seed=5)
+    src, tin, tout, sp, tp = O.synth_batch(5, 300, 280, seed=12, min_frac=0.3)
+    ls, lt = (~sp).sum(1).tolist(), (~tp).sum(1).tolist()
+    assert min(ls) < 200 < max(ls)
+    W, C = O.loss_weights(0.8)
+    ref_loss, ref_grads, _, _ = O.train_step_grads(sd, src, tin, tout, sp, tp, cfg["h"], W, C)
+
+    def engine():
+        m = ScoreTransformer(309, cfg["d"], cfg["h"], cfg["le"], cfg["ld"], cfg["ff"], cfg["maxlen"], 0.0, 0.0,
+                             compute_dtype="bf16").to(DEV)
+        m.load_state_dict(sd)
+        return TrainEngine(m.train(), lr=1e-3, eos_weight=0.8)
+
+    dev_b = [t.to(DEV) for t in (src, tin, tout, sp, tp)]
+    e_pad = engine()
+    e_pad.step(*dev_b, update=False)
+    s_pad = e_pad.sums.cpu()
+    e_pk = engine()
+    pk = PackedBatch.pack(dev_b[0], dev_b[1], dev_b[2], ls, lt)
+    assert pk.rows_s % 128 == 0 and pk.n_s == sum(ls) and pk.rows_s - pk.n_s < 128
+    # the collate kernel moved exactly the non-pad tokens, in order
+    assert pk.src_ids[: pk.n_s].cpu().tolist() == src[~sp].tolist()
+    assert pk.tgt_out[: pk.n_t].cpu().tolist() == tout[~tp].tolist()
+    assert pk.pos_t[: pk.n_t].cpu().tolist() == [i for n in lt for i in range(n)]
+    e_pk.step_packed(pk, update=False)
+    s_pk = e_pk.sums.cpu()
+    torch.testing.assert_close(s_pk[1], s_pad[1], rtol=0, atol=0)                 # the normaliser counts the same targets
+    assert abs(float(s_pk[0] / s_pk[1]) - float(s_pad[0] / s_pad[1])) < 2e-3 * abs(float(s_pad[0] / s_pad[1]))
+    assert abs(float(s_pk[0] / s_pk[1]) - ref_loss.item()) < 2e-2 * abs(ref_loss.item())
+    for n, g in e_pad.grads.grads.items():
+        a, b, r = e_pk.grads.grads[n].cpu().flatten(), g.cpu().flatten(), ref_grads[n].flatten()
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+        assert cos > 0.9995, (n, cos)
+        assert (a - b).abs().max().item() < 3e-2 * max(b.abs().max().item(), 1e-12), n
+        assert torch.nn.functional.cosine_similarity(a, r, dim=0).item() > 0.995, n
+    # captured packed step with the collate inside the graph: replay on two different ragged batches
+    e_g = engine()
+    e_g.lr = 0.0                                    # (the learning rate is baked into the captured Adam launch)
+    e_g.capture_packed(5, 5 * 300, 5 * 280, 300, 280)
+    for seed in (12, 13):
+        b = O.synth_batch(5, 300, 280, seed=seed, min_frac=0.3)
+        bl, tl = (~b[3]).sum(1).tolist(), (~b[4]).sum(1).tolist()
+        e_g.lr = 0.0
+        e_g.step_graph_packed(b[0].pin_memory(), b[1].pin_memory(), b[2].pin_memory(), bl, tl)
+        e_ref = engine()
+        e_ref.step(*[t.to(DEV) for t in b], update=False)
+        sg, sr = e_g.sums.cpu(), e_ref.sums.cpu()
+        assert float(sg[1]) == float(sr[1])
+        assert abs(float(sg[0] / sg[1]) - float(sr[0] / sr[1])) < 2e-3 * abs(float(sr[0] / sr[1]))
+    e_g.release_graph()
