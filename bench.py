@@ -323,7 +323,8 @@ def build_model(cfg, dtype, dev, dropout=0.1, seed=1234, world=1):
     return model
 
 
-def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e=False, profile=False, clocks=False):
+def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e=False, profile=False, clocks=False,
+                packed=True):
     """One training workload on every rank: `steps` timed steps after `warmup`, CUDA events, max over ranks."""
     from smer_music_generation_b200 import ops
     from smer_music_generation_b200.trainer import TrainEngine
@@ -338,11 +339,22 @@ def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e
     devb = [tuple(t.to(dev) for t in b) for b in host]
     ntok = [int((~b[3]).sum() + (~b[4]).sum()) for b in host]
     out = {"h2d": sum(t.numel() * t.element_size() for t in host[0])}
+    packed = packed and dtype == "bf16" and cfg["d"] // cfg["nhead"] == 64
+    out["packed"] = packed
+    lens = [((~b[3]).sum(1).tolist(), (~b[4]).sum(1).tolist()) for b in host]     # HOST lengths, as a collate step has them
+    if packed:
+        from smer_music_generation_b200.model import PackedBatch
+        up = lambda n: (n + 127) // 128 * 128
+        rows_s, rows_t = max(up(sum(l[0])) for l in lens), max(up(sum(l[1])) for l in lens)
+        out["h2d"] = sum(t.numel() * t.element_size() for t in host[0][:3]) + 8 * (B + 1)
     launches_per_step = None
     if use_graph:
         l0 = ops.LAUNCHES
         try:
-            eng.capture(B, S, T)                          # warm-up pass + capture (two passes of launches)
+            if packed:
+                eng.capture_packed(B, rows_s, rows_t, S, T)
+            else:
+                eng.capture(B, S, T)                      # warm-up pass + capture (two passes of launches)
             launches_per_step = (ops.LAUNCHES - l0 - 1) // 2 + 3  # + arena memset, loss-sum memset, counter bump
         except Exception as e:                            # e.g. a collective that refuses capture: run eagerly
             if rank == 0:
@@ -353,7 +365,16 @@ def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e
         flag = torch.tensor([1 if use_graph else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         use_graph = bool(flag.item())
-    step = (lambda b: eng.step_graph(*b)) if use_graph else (lambda b: eng.step(*b))
+    if packed:
+        if use_graph:
+            stepi = lambda bt, i: eng.step_graph_packed(bt[0], bt[1], bt[2], lens[i][0], lens[i][1])
+        else:
+            stepi = lambda bt, i: eng.step_packed(PackedBatch.pack(bt[0].to(dev, non_blocking=True), bt[1].to(dev, non_blocking=True),
+                                                                   bt[2].to(dev, non_blocking=True), lens[i][0], lens[i][1]))
+    else:
+        stepi = (lambda bt, i: eng.step_graph(*bt)) if use_graph else (lambda bt, i: eng.step(*tuple(t.to(dev, non_blocking=True) for t in bt)))
+    step = lambda b: stepi(b[0], b[1])
+    devb = [(b, i) for i, b in enumerate(devb)]
     for i in range(warmup):
         step(devb[i % nb])
     ctx.barrier()
@@ -380,10 +401,7 @@ def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e
         toks2 = 0
         loss_host = torch.zeros(steps, 16, dtype=torch.float64).pin_memory()
         for i in range(steps):
-            if use_graph:
-                eng.step_graph(*host[i % nb])             # pinned host batch -> H2D into the step's input buffers
-            else:
-                eng.step(*tuple(t.to(dev, non_blocking=True) for t in host[i % nb]))
+            stepi(host[i % nb], i % nb)                   # pinned host batch -> H2D into the step's input buffers
             loss_host[i].copy_(eng.sums, non_blocking=True)   # D2H of the step's 16 loss sums (128 B), every step
             toks2 += ntok[i % nb]
         e1.record()
@@ -399,7 +417,10 @@ def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e
         for _ in range(3):               # three profiled steps, per family the fastest (a starved device inflates a pass)
             ops.PROFILE = {}
             torch.cuda._sleep(int(8e7))  # ~40 ms head start: the host enqueues the whole step ahead of the device, so the
-            eng.step(*devb[0])           # events bracket device execution only, not launch latency
+            if packed:                   # events bracket device execution only, not launch latency
+                eng.step_packed(PackedBatch.pack(devb[0][0][0], devb[0][0][1], devb[0][0][2], lens[0][0], lens[0][1]))
+            else:
+                eng.step(*devb[0][0])
             torch.cuda.synchronize()
             one = summarize_profile(ops.PROFILE)
             prof = one if prof is None else {k: (one[k] if one[k]["ms"] < prof[k]["ms"] else prof[k]) for k in one}
@@ -572,7 +593,7 @@ def run_train(args, ctx):
     B, S, T = args.batch, args.seq, args.tgt
     cfg = dict(CFG)
     r = timed_train(ctx, cfg, args.dtype, B, S, T, args.steps, args.warmup, ctx.pg, use_graph=not args.no_graph, e2e=True,
-                    profile=True, clocks=True)
+                    profile=True, clocks=True, packed=not args.padded)
     prof = r["profile"]
     pk = peaks()
     tot_ms = sum(v["ms"] for v in prof.values())
@@ -612,6 +633,8 @@ def run_train(args, ctx):
                                    f"train step fwd+loss+bwd+Adam, dropout 0.1, B{B}/GPU x S{S} (+T{T}), suffix padding "
                                    f"U[0.75L,L], tokens counted = non-pad src+tgt",
                        "l2": "working set per step (~3.5 GB activations) >> 126 MB L2; 4 rotating input batches",
+                       "layout": ("padding-free: packed rows + cu_seqlens, the collate (pad removal) runs on the GPU inside the step"
+                                  if r["packed"] else "padded (B, L) batches"),
                        "parallelism": f"dp{world}", "global_batch": B * world,
                        "launch": "whole step captured in one CUDA graph, replayed per step" if r["use_graph"] else "eager launches"},
             "clocks": r["clocks"],
@@ -642,6 +665,13 @@ def run_train(args, ctx):
         torch.cuda.empty_cache()
 
     sub("e2e_module_api", lambda: module_api_record(ctx, cfg, args.dtype, r["host"], r["ntok"]), world == 1 and not args.no_module_api)
+
+    def padded():
+        q = timed_train(ctx, cfg, args.dtype, B, S, T, 5, 3, ctx.pg, use_graph=not args.no_graph, packed=False)
+        return {"workload": "the same batches in the padded (B, L) layout (12.5 % of the rows are padding)", "value": q["value"],
+                "unit": "tokens/s", "ms_per_step": q["ms_per_step"], "loss": q["loss"]}
+
+    sub("padded_layout", padded, r["packed"])
 
     def c3():
         # configs[2]'s per-GPU shape, with the gradient all-reduce (N > 1) and without it (the same rank alone)
@@ -787,6 +817,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-module-api", action="store_true")
+    ap.add_argument("--padded", action="store_true", help="headline in the padded (B, L) layout instead of packed rows")
     ap.add_argument("--skip", default="", help="comma list of sub-records to skip: decode,c3,c5_attention,c1,torch_gpu_baseline,dp_overhead")
     ap.add_argument("--d-model", type=int, default=512)
     ap.add_argument("--nhead", type=int, default=8)
