@@ -264,7 +264,11 @@ class InfillDecoder:
         ff = m.dim_feedforward
         mk = lambda c, t=None: torch.empty(n, c, dtype=t or dt, device=dev)
         self.buf = dict(x=mk(d), qkv=mk(3 * d), o=mk(d), proj=mk(d), y1=mk(d), z=mk(d), q2=mk(d), o2=mk(d), y2=mk(d),
-                        h=mk(ff), f=mk(d), y3=mk(d), yo=mk(d), logits=mk(m.vpad, torch.float32))
+                        h=mk(ff), f=mk(d), y3=mk(d), yo=mk(d), logits=mk(m.vpad, torch.float32), xres=mk(d), z3=mk(d))
+        # small batches take the small-M projections with fused LayerNorm prologues (SMER_DECODE_SMALL=0/1 overrides)
+        import os
+        env = os.environ.get("SMER_DECODE_SMALL")
+        self.small = dt == torch.bfloat16 and d % 128 == 0 and ff % 128 == 0 and d <= 1024 and (n <= 256 if env is None else env == "1")
         self.graph = None
 
     def _setup(self, pieces, targets, nwd, seq_base):
@@ -342,8 +346,70 @@ class InfillDecoder:
             e1.record(torch.cuda.current_stream())
             prof.append(("cross" if new_k is None else "self", e0, e1))
 
+    def _step_small(self):
+        """The decode step for small batches (n <= 256 pieces per GPU, bf16): every projection through the small-M kernel
+        (a 64-row x 8-column slab per CTA, so that even a [n, 512] x [512, 512] product covers the GPU) with the LayerNorms
+        fused into the prologue of the product that consumes them -- 36 launches per token instead of 48."""
+        m, b = self.m, self.buf
+        d = m.d_model
+        n, L, S = self.n, self.max_len, self.S
+        lib = K.lib()
+        K.check(lib.smer_decode_embed(self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.fed_len.data_ptr(),
+                                      self.done.data_ptr(), self.pos.data_ptr(), m.embedding.weight.data_ptr(),
+                                      m.pos_enc.pe.data_ptr(), b["x"].data_ptr(), K.dt(b["x"]), n, L, d, m.vocab_size,
+                                      math.sqrt(d), K.stream()), "decode_embed")
+        lin = ops.decode_linear
+        x_in, prev_ln = b["x"], None                  # layer input: rows as they are, or pre-LN sums + that LayerNorm
+        launches = 1
+        for i, lp in enumerate(self.layer_p):
+            sa, ca = lp.sa, lp.ca
+            if prev_ln is None:
+                lin(x_in, sa.w, b["qkv"], bias=sa.b)
+                resid = x_in
+            else:
+                lin(x_in, sa.w, b["qkv"], bias=sa.b, ln=prev_ln, ln_out=b["xres"])
+                resid = b["xres"]
+            qkv, kv = b["qkv"], self.self_kv[i]
+            self._decode_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], kv[:, :, :d], kv[:, :, d:], b["o"], self.pos,
+                              None, 2 * d, L * 2 * d, L, 0)
+            lin(b["o"], sa.wo, b["z"], bias=sa.bo, resid=resid)                       # z1 = x + SelfAttn(x)
+            lin(b["z"], ca.w[:d], b["q2"], bias=ca.b[:d], ln=lp.ln[0], ln_out=b["y1"])  # y1 = LN1(z1); q = y1 Wq
+            ckv = self.cross[i]
+            self._decode_attn(b["q2"], None, None, ckv[:, :d], ckv[:, d:], b["o2"], self.src_len, None, 2 * d,
+                              S * 2 * d, S, 0)
+            lin(b["o2"], ca.wo, b["z"], bias=ca.bo, resid=b["y1"])                    # z2 = y1 + CrossAttn
+            lin(b["z"], lp.w1, b["h"], bias=lp.b1, relu=True, ln=lp.ln[1], ln_out=b["y2"])   # y2 = LN2(z2); h = relu(y2 W1)
+            lin(b["h"], lp.w2, b["z3"], bias=lp.b2, resid=b["y2"])                    # z3 = y2 + FFN
+            x_in, prev_ln = b["z3"], lp.ln[2]
+            launches += 8
+        dn = m.transformer.decoder.norm
+        ops.layernorm_fwd(x_in, None, prev_ln[0], prev_ln[1], None, b["y3"], None, None)     # LN3 of the last layer
+        lin(b["y3"], self.fc_p[0], b["logits"], bias=self.fc_p[1], ln=(dn.weight.detach(), dn.bias.detach()))
+        self._sample()
+        self.launches_per_step = launches + 3
+
+    def _sample(self):
+        m, b = self.m, self.buf
+        n, L = self.n, self.max_len
+        a = K.SampleArgs()
+        a.logits, a.ld, a.n_seq, a.V = b["logits"].data_ptr(), b["logits"].stride(0), n, m.vocab_size
+        a.mode, a.temperature, a.top_p, a.top_k = self.mode, self.temperature, self.top_p, self.top_k
+        a.seed, a.seq_base, a.step_base = self.seed, self.seq_base, 0
+        a.state, a.targets, a.nwd, a.max_spans = self.state.data_ptr(), self.targets.data_ptr(), self.nwd.data_ptr(), self.max_spans
+        a.raw_flags = a.raw_only_lo = a.raw_only_hi = None
+        a.tok_buf, a.cur_len, a.span_start = self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.span_start.data_ptr()
+        a.span_idx, a.fed_len, a.n_spans = self.span_idx.data_ptr(), self.fed_len.data_ptr(), self.n_spans.data_ptr()
+        a.done, a.gen_count, a.control_bitmap = self.done.data_ptr(), self.gen_count.data_ptr(), self.bitmap.data_ptr()
+        a.max_len, a.max_span = L, self.max_span
+        a.out_token = a.out_probs = None
+        a.trace_masked = self.trace_masked.data_ptr() if self.trace_masked is not None else None
+        a.trace_span = self.trace_span.data_ptr() if self.trace_masked is not None else None
+        K.check(K.lib().smer_sample_masked(C.byref(a), K.stream()), "sample_masked")
+
     def _step(self, step_idx_base: int):
         """One token for every unfinished piece.  All launches on the current stream; no sync."""
+        if self.small:
+            return self._step_small()
         m, b = self.m, self.buf
         d = m.d_model
         n, L, S = self.n, self.max_len, self.S
@@ -377,20 +443,7 @@ class InfillDecoder:
         dn = m.transformer.decoder.norm
         ops.layernorm_fwd(x, None, dn.weight.detach(), dn.bias.detach(), None, b["yo"], None, None)
         ops.gemm_nt(b["yo"], self.fc_p[0], b["logits"], bias=self.fc_p[1])
-        a = K.SampleArgs()
-        a.logits, a.ld, a.n_seq, a.V = b["logits"].data_ptr(), b["logits"].stride(0), n, m.vocab_size
-        a.mode, a.temperature, a.top_p, a.top_k = self.mode, self.temperature, self.top_p, self.top_k
-        a.seed, a.seq_base, a.step_base = self.seed, self.seq_base, 0
-        a.state, a.targets, a.nwd, a.max_spans = self.state.data_ptr(), self.targets.data_ptr(), self.nwd.data_ptr(), self.max_spans
-        a.raw_flags = a.raw_only_lo = a.raw_only_hi = None
-        a.tok_buf, a.cur_len, a.span_start = self.tok_buf.data_ptr(), self.cur_len.data_ptr(), self.span_start.data_ptr()
-        a.span_idx, a.fed_len, a.n_spans = self.span_idx.data_ptr(), self.fed_len.data_ptr(), self.n_spans.data_ptr()
-        a.done, a.gen_count, a.control_bitmap = self.done.data_ptr(), self.gen_count.data_ptr(), self.bitmap.data_ptr()
-        a.max_len, a.max_span = L, self.max_span
-        a.out_token = a.out_probs = None
-        a.trace_masked = self.trace_masked.data_ptr() if self.trace_masked is not None else None
-        a.trace_span = self.trace_span.data_ptr() if self.trace_masked is not None else None
-        K.check(lib.smer_sample_masked(C.byref(a), K.stream()), "sample_masked")
+        self._sample()
         self.launches_per_step = launches + 3
 
     def profile_step(self):

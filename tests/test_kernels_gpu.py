@@ -564,3 +564,32 @@ def test_sampler_empirical_histogram(dev, oracle):
     hist = np.bincount(tok, minlength=309) / n
     assert 0.5 * np.abs(hist - q).sum() < 0.06
     assert hist[3:146].sum() == 0
+
+
+# ---------------------------------------------------------------------------------------- decode: small-M linear
+@pytest.mark.parametrize("M,N,K,mode", [(5, 512, 512, "plain"), (130, 1536, 512, "ln"), (64, 320, 512, "ln_f32"),
+                                        (128, 512, 2048, "resid"), (200, 2048, 512, "ln_relu"), (1, 512, 512, "ln_resid")])
+def test_decode_linear_vs_torch(dev, M, N, K, mode):
+    """csrc/decode_linear.cu: out = epi(LN?(a) @ w^T + b) for the decode step's few rows, every epilogue / prologue."""
+    ops, Kc = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g).to(dev).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    resid = torch.randn(M, N, generator=g).to(dev).bfloat16() if "resid" in mode else None
+    gamma, beta = (torch.rand(K, generator=g) + 0.5).to(dev), (torch.randn(K, generator=g) * 0.1).to(dev)
+    ln = (gamma, beta) if mode.startswith("ln") else None
+    out = torch.empty(M, N, dtype=torch.float32 if mode == "ln_f32" else torch.bfloat16, device=dev)
+    y = torch.empty(M, K, dtype=torch.bfloat16, device=dev) if ln else None
+    ops.decode_linear(a, w, out, bias=bias, resid=resid, relu="relu" in mode, ln=ln, ln_out=y)
+    x = a.float()
+    if ln:
+        x = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5)
+        assert rel(y, x) < 1e-2
+        x = x.bfloat16().float()                    # the kernel feeds the tensor cores the bf16-rounded normalised rows
+    ref = x @ w.float().t() + bias
+    if "relu" in mode:
+        ref = ref.relu()
+    if resid is not None:
+        ref = ref + resid.float()
+    assert rel(out, ref) < (2e-3 if mode == "ln_f32" else 1e-2)
