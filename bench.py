@@ -57,7 +57,7 @@ def peaks():
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))
         return t[kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
