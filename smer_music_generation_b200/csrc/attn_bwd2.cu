@@ -61,6 +61,7 @@ struct Params {
   uint64_t seed, site;
   const unsigned long long* seed_dev;
   const int *cu_q, *cu_k;    // padding-free layout (smer_b200.h) or NULL
+  long long k_rows;          // rows of the packed K / V (and dK / dV) buffers
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -70,9 +71,6 @@ __device__ __forceinline__ float ex2(float x) {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 template <bool DROP>
@@ -197,6 +195,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         ptx::tma_wait_group0();                         // reductions performed before the CTA retires
       }
       __syncwarp();
+    } else if (p.cu_q && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      // warp 19 of the first CTA: the ghost rows past the last sequence of a packed batch belong to no key tile; the
+      // weight-gradient GEMM sums over all rows, so their dK / dV must be zero
+      const int first = p.cu_k[p.B];
+      for (long long i = (long long)first * (p.H * DH / 8) + lane; i < p.k_rows * (p.H * DH / 8); i += 32) {
+        const long long row = i / (p.H * DH / 8);
+        const int c8 = (int)(i - row * (p.H * DH / 8));
+        *reinterpret_cast<uint4*>(p.dk + row * p.lddk + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(p.dv + row * p.lddv + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   } else {
     // ------------------------------------------------------------------ element-wise threads
@@ -380,7 +388,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // D[b,h,i] = sum_c dO[i, h*64 + c] * O[i, h*64 + c]: 8 threads per (row, head), 16-byte loads
 __global__ void __launch_bounds__(256)
 attn_dsum_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ dout, long long lddo,
-                 float* __restrict__ dsum, long long rows, int H, int Lq, const int* __restrict__ cu_q, int B) {
+                 float* __restrict__ dsum, long long rows, int H, int Lq, const int* __restrict__ cu_q, int B,
+                 float* __restrict__ dq_acc) {
   const long long t = blockIdx.x * 256ll + threadIdx.x;
   const long long grp = t >> 3;                       // (row, head)
   const int sub = (int)(t & 7);
@@ -389,6 +398,10 @@ attn_dsum_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restri
   if (grp < total) {
     const long long row = grp / H;
     const int hh = (int)(grp % H);
+    // this thread's 8 columns of the fp32 dQ accumulation buffer start the backward at zero (saves a separate memset pass)
+    float4* z = reinterpret_cast<float4*>(dq_acc + row * ((long long)H * DH) + hh * DH + sub * 8);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint4 ov = *reinterpret_cast<const uint4*>(o + row * ldo + hh * DH + sub * 8);
     const uint4 gv = *reinterpret_cast<const uint4*>(dout + row * lddo + hh * DH + sub * 8);
     f32x2 a2 = pack2(0.f, 0.f);
@@ -474,7 +487,7 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
   p.thr2 = a->dropout_p > 0.f ? attn_dropout_threshold(a->dropout_p) * 0x10001u : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
-  p.cu_q = a->cu_q; p.cu_k = a->cu_k;
+  p.cu_q = a->cu_q; p.cu_k = a->cu_k; p.k_rows = a->k_rows;
   static int attr_dev_mask = 0;
   int dev = 0;
   SMER_CUDA(cudaGetDevice(&dev));
@@ -489,11 +502,10 @@ int smer_attn_bwd2_launch(const smer_attn_args* a, void* stream) {
   if ((rc = smer_make_tmap_bf16(&tdo, a->dout, dcols, rq, a->lddo, DH, BM))) return rc;
   if ((rc = smer_make_tmap_bf16(&tk, a->k, dcols, rk, a->ldk, DH, BN))) return rc;
   if ((rc = smer_make_tmap_bf16(&tv, a->v, dcols, rk, a->ldv, DH, BN))) return rc;
-  SMER_CUDA(cudaMemsetAsync(a->dq_accum, 0, (size_t)rq * dcols * sizeof(float), st));
   {
     const long long threads = rq * a->H * 8;
     attn_dsum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const bf16*)a->o, a->ldo, (const bf16*)a->dout, a->lddo,
-                                                                        a->dsum, rq, a->H, a->Lq, a->cu_q, a->B);
+                                                                        a->dsum, rq, a->H, a->Lq, a->cu_q, a->B, (float*)a->dq_accum);
   }
   dim3 grid((a->Lk + BN - 1) / BN, a->H, a->B);
   if (p.thr2) attn_bwd2_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(tq, tdo, tk, tv, tdq, p);

@@ -58,6 +58,7 @@ struct Params {
   const unsigned long long* seed_dev;
   int npair, items;        // query-tile pairs per (b,h); npair * H * B work items
   const int *cu_q, *cu_k;  // padding-free layout (smer_b200.h): per-sequence row ranges of the packed buffers, or NULL
+  long long q_rows;        // rows of the packed Q (and O) buffers
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -244,6 +245,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     __syncwarp();
+  } else if (p.cu_q && blockIdx.x == 0) {
+    // warps 18 / 19 of the first CTA: the ghost rows past the last sequence of a packed batch are written by no item; the
+    // projections that follow read every row, so they must hold finite values (zeros)
+    const int first = p.cu_q[p.B];
+    const int cols8 = p.H * DH / 8;
+    for (long long i = (long long)first * cols8 + (warp - 18) * 32 + lane; i < p.q_rows * cols8; i += 64) {
+      const long long row = i / cols8;
+      *reinterpret_cast<uint4*>(p.o + row * p.ldo + (i - row * cols8) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   } else {
     // ------------------------------------------------------------------ softmax: chain q, one thread per query row
@@ -451,7 +461,7 @@ int smer_attn_fwd2_launch(const smer_attn_args* a, void* stream) {
   p.thr2 = a->dropout_p > 0.f ? attn_dropout_threshold(a->dropout_p) * 0x10001u : 0u;
   p.inv_keep = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
   p.seed = a->seed; p.site = a->site; p.seed_dev = smer_seed_dev();
-  p.cu_q = a->cu_q; p.cu_k = a->cu_k;
+  p.cu_q = a->cu_q; p.cu_k = a->cu_k; p.q_rows = a->q_rows;
   p.npair = (a->Lq + 2 * BM - 1) / (2 * BM);
   const long long items = (long long)p.npair * a->H * a->B;
   SMER_CHECK_ARG(items < (1ll << 31), "smer_attn_fwd_tc: too many work items");

@@ -495,8 +495,6 @@ class _Run:
             ops.gemm_nt(xkv, ap.w[d:3 * d], kvbuf, bias=ap.b[d:])
             q, k, v = qkv, kvbuf[:, :d], kvbuf[:, d:]
         o = self.new(rq, d)
-        if pk is not None:
-            ops.zero_tail_rows(o, cu_q)           # ghost rows belong to no sequence: the kernels never write them
         lse = torch.empty(H * rq if pk is not None else B * H * Lq, dtype=torch.float32, device=self.dev)
         a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=key_pad, kv_len=kv_len,
                           add_mask=add_mask, dropout_p=self.td, seed=self.seed, site=site_p, cu_q=cu_q, cu_k=cu_k)
@@ -531,15 +529,11 @@ class _Run:
             dqkv = self.new(rq, 3 * d)
             q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
             dq, dk, dv = dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:]
-            if pk is not None:
-                ops.zero_tail_rows(dqkv, cu_q)    # ghost rows: the backward kernel writes dK / dV rows of real keys only
         else:
             dqkv = self.new(rq, d)
             dkv = self.new(kvbuf.shape[0], 2 * d)
             q, k, v = qkv, kvbuf[:, :d], kvbuf[:, d:]
             dq, dk, dv = dqkv, dkv[:, :d], dkv[:, d:]
-            if pk is not None:
-                ops.zero_tail_rows(dkv, cu_k)
         gw, gb = grads[n + "in_proj_weight"], grads[n + "in_proj_bias"]
         # in_proj_bias gradient = column sums of dq | dk | dv, accumulated by the attention backward kernels
         a = ops.attn_args(q, k, v, o, B, H, Lq, Lk, dh, lse=lse, causal=causal, key_pad=key_pad, kv_len=kv_len,
