@@ -173,8 +173,11 @@ static int decode_launch(const smer_decode_attn_args& a, cudaStream_t st) {
     case 32: decode_attn_kernel<T, 32, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a); break;
     case 64:
       // the self-attention cache (new_k given) holds at most cache_len keys, usually a few hundred:
-      // one warp per (piece, head) avoids paying a 128-thread CTA's fixed costs for a handful of keys
-      if (a.new_k && a.cache_len <= 2048 && a.splits == 1)
+      // one warp per (piece, head) avoids paying a 128-thread CTA's fixed costs for a handful of keys -- as long as
+      // there are enough (piece, head) pairs to fill the GPU with warps; with few pieces a single warp walking a
+      // several-hundred-key cache is latency-bound (128 pieces: +30 us per layer at 500 cached tokens), so those
+      // take the 128-thread CTA (16 key rows in flight)
+      if (a.new_k && a.cache_len <= 2048 && a.splits == 1 && (long long)a.n_seq * a.H > 4096)
         decode_attn_kernel<T, 64, DEC_THREADS_SHORT><<<grid, DEC_THREADS_SHORT, 0, st>>>(a);
       else
         decode_attn_kernel<T, 64, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a);
