@@ -209,11 +209,15 @@ int smer_embed_step(const int64_t* ids, const int* pos, const float* emb, const 
 /* Small-M linear layer of the decode step (bf16 operands, M = pieces being decoded): out = epi(LN?(a) . w^T + bias),
  * w is [N, K] row-major like nn.Linear.weight (transformer.py:362-364).  Epilogues: relu, or + resid (both bf16 out), or
  * fp32 out (the vocabulary projection, model.py:106).  ln_gamma / ln_beta non-NULL: `a` holds pre-normalisation sums and
- * the rows are LayerNorm-ed on the fly (eps as nn.LayerNorm); ln_out (nullable) receives the normalised rows. */
+ * the rows are LayerNorm-ed on the fly (eps as nn.LayerNorm); ln_out (nullable) receives the normalised rows.
+ * ln2_gamma / ln2_beta non-NULL: a second LayerNorm over the (bf16-rounded) result of the first -- the last decoder
+ * layer's norm3 followed by the decoder's final norm (transformer.py:469, 286-287) ahead of the vocabulary projection.
+ * Launched with programmatic stream serialization: the weight loads start while the previous kernel of the stream
+ * drains (see smer_launch_pdl in csrc/common.cuh; SMER_PDL=0 disables it). */
 int smer_decode_linear(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* resid,
                        long long ldr, void* out, long long ldo, int out_dtype, int M, int N, int K, int relu,
-                       const float* ln_gamma, const float* ln_beta, void* ln_out, long long ld_ln_out, float eps,
-                       void* stream);
+                       const float* ln_gamma, const float* ln_beta, void* ln_out, long long ld_ln_out,
+                       const float* ln2_gamma, const float* ln2_beta, float eps, void* stream);
 
 typedef struct smer_sample_args {
   const float* logits;        /* [n_seq, ld] last-position logits                             */

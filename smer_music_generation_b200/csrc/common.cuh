@@ -26,6 +26,31 @@ void smer_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
+// Programmatic dependent launch for the kernels of the decode step (a chain of ~36 short launches per token inside a CUDA
+// graph): a kernel launched through smer_launch_pdl may be scheduled as soon as every CTA of its predecessor has executed
+// pdl_trigger(), and must execute pdl_wait() before it reads or writes anything a predecessor touches -- until then it may
+// only set itself up and prefetch data no kernel of the chain writes (weights).  pdl_wait() returns once the predecessor
+// grid has completed and its writes are visible, so the chain stays strictly ordered; only launch latency and prologues
+// overlap.  SMER_PDL=0 in the environment turns the attribute off (plain stream order).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool smer_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SMER_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t smer_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = smer_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define SMER_CHECK_LAUNCH(name)                                              \
   do {                                                                       \
     cudaError_t e__ = cudaPeekAtLastError();                                 \

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(smer_decode_attn_a
   __shared__ float sm_m[DEC_GROUPS], sm_l[DEC_GROUPS];
   __shared__ float sm_acc[DEC_GROUPS][DH];
   int h = blockIdx.x, s = blockIdx.y, sp = blockIdx.z;
+  pdl_trigger();
+  pdl_wait();
   if (a.done && a.done[s]) return;                // a finished piece: nothing is appended, its K/V is not streamed
   int tid = threadIdx.x;
   int grp = tid / LPK, lig = tid % LPK;
@@ -146,6 +148,8 @@ __global__ void __launch_bounds__(THREADS) decode_attn_kernel(smer_decode_attn_a
 template <typename T, int DH>
 __global__ void decode_merge_kernel(smer_decode_attn_args a, int H) {
   int h = blockIdx.x, s = blockIdx.y, c = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (a.done && a.done[s]) return;
   const float* w = a.workspace + ((long long)s * H + h) * a.splits * (DH + 2);
   float M = -INFINITY;
@@ -169,8 +173,8 @@ template <typename T>
 static int decode_launch(const smer_decode_attn_args& a, cudaStream_t st) {
   dim3 grid(a.H, a.n_seq, a.splits);
   switch (a.dh) {
-    case 16: decode_attn_kernel<T, 16, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a); break;
-    case 32: decode_attn_kernel<T, 32, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a); break;
+    case 16: smer_launch_pdl(decode_attn_kernel<T, 16, DEC_THREADS>, grid, dim3(DEC_THREADS), 0, st, a); break;
+    case 32: smer_launch_pdl(decode_attn_kernel<T, 32, DEC_THREADS>, grid, dim3(DEC_THREADS), 0, st, a); break;
     case 64:
       // the self-attention cache (new_k given) holds at most cache_len keys, usually a few hundred:
       // one warp per (piece, head) avoids paying a 128-thread CTA's fixed costs for a handful of keys -- as long as
@@ -178,18 +182,18 @@ static int decode_launch(const smer_decode_attn_args& a, cudaStream_t st) {
       // several-hundred-key cache is latency-bound (128 pieces: +30 us per layer at 500 cached tokens), so those
       // take the 128-thread CTA (16 key rows in flight)
       if (a.new_k && a.cache_len <= 2048 && a.splits == 1 && (long long)a.n_seq * a.H > 4096)
-        decode_attn_kernel<T, 64, DEC_THREADS_SHORT><<<grid, DEC_THREADS_SHORT, 0, st>>>(a);
+        smer_launch_pdl(decode_attn_kernel<T, 64, DEC_THREADS_SHORT>, grid, dim3(DEC_THREADS_SHORT), 0, st, a);
       else
-        decode_attn_kernel<T, 64, DEC_THREADS><<<grid, DEC_THREADS, 0, st>>>(a);
+        smer_launch_pdl(decode_attn_kernel<T, 64, DEC_THREADS>, grid, dim3(DEC_THREADS), 0, st, a);
       break;
     default: smer_set_error("smer_decode_attn: head dim %d unsupported (16/32/64)", a.dh); return SMER_ERR_UNSUPPORTED;
   }
   if (a.splits > 1) {
     dim3 g2(a.H, a.n_seq);
     switch (a.dh) {
-      case 16: decode_merge_kernel<T, 16><<<g2, 16, 0, st>>>(a, a.H); break;
-      case 32: decode_merge_kernel<T, 32><<<g2, 32, 0, st>>>(a, a.H); break;
-      case 64: decode_merge_kernel<T, 64><<<g2, 64, 0, st>>>(a, a.H); break;
+      case 16: smer_launch_pdl(decode_merge_kernel<T, 16>, g2, dim3(16), 0, st, a, a.H); break;
+      case 32: smer_launch_pdl(decode_merge_kernel<T, 32>, g2, dim3(32), 0, st, a, a.H); break;
+      case 64: smer_launch_pdl(decode_merge_kernel<T, 64>, g2, dim3(64), 0, st, a, a.H); break;
     }
   }
   return SMER_OK;
@@ -273,6 +277,8 @@ __global__ void decode_embed_kernel(const long long* __restrict__ tok_buf, const
                                     const float* __restrict__ emb, const float* __restrict__ pe, T* __restrict__ out,
                                     int max_len, int d4, int V, float scale) {
   const int s = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (done && done[s]) return;
   int p = cur_len[s] - 1;
   if (fed_len) p = min(p, fed_len[s]);
@@ -297,9 +303,9 @@ extern "C" int smer_decode_embed(const int64_t* tok_buf, const int* cur_len, con
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = d / 4 < 128 ? (d / 4 + 31) / 32 * 32 : 128;
   if (out_dtype == SMER_DT_F32)
-    decode_embed_kernel<float><<<n_seq, threads, 0, st>>>((const long long*)tok_buf, cur_len, fed_len, done, pos, emb, pe, (float*)out, max_len, d / 4, V, scale);
+    smer_launch_pdl(decode_embed_kernel<float>, dim3(n_seq), dim3(threads), 0, st, (const long long*)tok_buf, cur_len, fed_len, done, pos, emb, pe, (float*)out, max_len, d / 4, V, scale);
   else
-    decode_embed_kernel<bf16><<<n_seq, threads, 0, st>>>((const long long*)tok_buf, cur_len, fed_len, done, pos, emb, pe, (bf16*)out, max_len, d / 4, V, scale);
+    smer_launch_pdl(decode_embed_kernel<bf16>, dim3(n_seq), dim3(threads), 0, st, (const long long*)tok_buf, cur_len, fed_len, done, pos, emb, pe, (bf16*)out, max_len, d / 4, V, scale);
   SMER_CHECK_LAUNCH("smer_decode_embed");
   return SMER_OK;
 }

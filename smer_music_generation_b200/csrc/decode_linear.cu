@@ -32,6 +32,7 @@ struct Args {
   const bf16* resid; long long ldr;
   void* out; long long ldo;
   const float *gamma, *beta;      // LN prologue
+  const float *gamma2, *beta2;    // a second LayerNorm applied to the result of the first (last layer's LN3, then the decoder's final norm)
   bf16* y; long long ldy;         // LN prologue: normalised rows (nullable)
   int M, N, K;
   float eps;
@@ -85,20 +86,31 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(Args p) {
   const bool write_y = LN && p.y != nullptr && blockIdx.x == 0;
 
   float c[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-  float mean_a = 0.f, rstd_a = 1.f, mean_b = 0.f, rstd_b = 1.f;
+  pdl_trigger();
   for (int s0 = 0; s0 < nsteps; s0 += DL_CHUNK) {
     uint4 va[DL_CHUNK], vb[DL_CHUNK], vw[DL_CHUNK], vx[DL_CHUNK];
 #pragma unroll
     for (int u = 0; u < DL_CHUNK; ++u) {
       if (s0 + u < nsteps) {
-        va[u] = *reinterpret_cast<const uint4*>(arow + (s0 + u) * 32);
-        vb[u] = *reinterpret_cast<const uint4*>(brow + (s0 + u) * 32);
         vw[u] = *reinterpret_cast<const uint4*>(wrow + (s0 + u) * 32);
         vx[u] = *reinterpret_cast<const uint4*>(wrow2 + (s0 + u) * 32);
       }
     }
-    if (LN) {
-      // (the launcher guarantees nsteps <= DL_CHUNK with a LayerNorm prologue: the whole K quarter is in registers)
+    // the weights above are written by no kernel of the decode chain, so their loads are already in flight while the
+    // previous launch drains; the activations are its output
+    if (s0 == 0) pdl_wait();
+#pragma unroll
+    for (int u = 0; u < DL_CHUNK; ++u) {
+      if (s0 + u < nsteps) {
+        va[u] = *reinterpret_cast<const uint4*>(arow + (s0 + u) * 32);
+        vb[u] = *reinterpret_cast<const uint4*>(brow + (s0 + u) * 32);
+      }
+    }
+    // (the launcher guarantees nsteps <= DL_CHUNK with a LayerNorm prologue: the whole K quarter is in registers)
+    for (int pass = 0; LN && pass < (p.gamma2 ? 2 : 1); ++pass) {
+      const float* gamma = pass ? p.gamma2 : p.gamma;
+      const float* beta = pass ? p.beta2 : p.beta;
+      if (pass) __syncthreads();                      // every warp has read the first pass's partial sums
       float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
 #pragma unroll
       for (int u = 0; u < DL_CHUNK; ++u)
@@ -119,16 +131,16 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(Args p) {
         tb += stat[q][rg * 16 + g + 8][0]; ub += stat[q][rg * 16 + g + 8][1];
       }
       const float inv_k = 1.f / p.K;
-      mean_a = ta * inv_k; mean_b = tb * inv_k;
-      rstd_a = rsqrtf(fmaxf(ua * inv_k - mean_a * mean_a, 0.f) + p.eps);
-      rstd_b = rsqrtf(fmaxf(ub * inv_k - mean_b * mean_b, 0.f) + p.eps);
+      const float mean_a = ta * inv_k, mean_b = tb * inv_k;
+      const float rstd_a = rsqrtf(fmaxf(ua * inv_k - mean_a * mean_a, 0.f) + p.eps);
+      const float rstd_b = rsqrtf(fmaxf(ub * inv_k - mean_b * mean_b, 0.f) + p.eps);
 #pragma unroll
       for (int u = 0; u < DL_CHUNK; ++u) {
         if (u < nsteps) {
           const int k = k_lo + u * 32 + 8 * t;
-          va[u] = ln_apply(va[u], mean_a, rstd_a, p.gamma, p.beta, k);
-          vb[u] = ln_apply(vb[u], mean_b, rstd_b, p.gamma, p.beta, k);
-          if (write_y) {
+          va[u] = ln_apply(va[u], mean_a, rstd_a, gamma, beta, k);
+          vb[u] = ln_apply(vb[u], mean_b, rstd_b, gamma, beta, k);
+          if (write_y && pass == 0) {
             if (r0 + g < p.M) *reinterpret_cast<uint4*>(p.y + (long long)(r0 + g) * p.ldy + k) = va[u];
             if (r0 + g + 8 < p.M) *reinterpret_cast<uint4*>(p.y + (long long)(r0 + g + 8) * p.ldy + k) = vb[u];
           }
@@ -181,7 +193,8 @@ __global__ void __launch_bounds__(DL_THREADS) decode_linear_kernel(Args p) {
 extern "C" int smer_decode_linear(const void* a, long long lda, const void* w, long long ldw, const float* bias,
                                   const void* resid, long long ldr, void* out, long long ldo, int out_dtype, int M, int N,
                                   int K, int relu, const float* ln_gamma, const float* ln_beta, void* ln_out,
-                                  long long ld_ln_out, float eps, void* stream) {
+                                  long long ld_ln_out, const float* ln2_gamma, const float* ln2_beta, float eps,
+                                  void* stream) {
   SMER_CHECK_ARG(a && w && out && M > 0 && N > 0 && K > 0, "smer_decode_linear: null args");
   SMER_CHECK_ARG(K % 128 == 0 && lda % 8 == 0 && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(w) & 15) == 0,
@@ -190,16 +203,18 @@ extern "C" int smer_decode_linear(const void* a, long long lda, const void* w, l
   SMER_CHECK_ARG(N % 2 == 0 && ldo % 2 == 0 && (!resid || ldr % 2 == 0), "smer_decode_linear: N and the output pitch must be even");
   SMER_CHECK_ARG(!(relu && resid), "smer_decode_linear: ReLU and residual epilogues are exclusive");
   SMER_CHECK_ARG((ln_gamma == nullptr) == (ln_beta == nullptr), "smer_decode_linear: gamma and beta come together");
+  SMER_CHECK_ARG((ln2_gamma == nullptr) == (ln2_beta == nullptr) && (!ln2_gamma || ln_gamma),
+                 "smer_decode_linear: the second LayerNorm needs both its parameters and a first LayerNorm");
   SMER_CHECK_ARG(!ln_out || (ld_ln_out % 8 == 0 && (reinterpret_cast<uintptr_t>(ln_out) & 15) == 0), "smer_decode_linear: ln_out rows must be 16-byte aligned");
   Args p;
   p.a = (const bf16*)a; p.lda = lda; p.w = (const bf16*)w; p.ldw = ldw; p.bias = bias;
   p.resid = (const bf16*)resid; p.ldr = ldr; p.out = out; p.ldo = ldo;
-  p.gamma = ln_gamma; p.beta = ln_beta; p.y = (bf16*)ln_out; p.ldy = ld_ln_out;
+  p.gamma = ln_gamma; p.beta = ln_beta; p.gamma2 = ln2_gamma; p.beta2 = ln2_beta; p.y = (bf16*)ln_out; p.ldy = ld_ln_out;
   p.M = M; p.N = N; p.K = K; p.eps = eps;
   dim3 grid((N + DL_BN - 1) / DL_BN, (M + DL_BM - 1) / DL_BM);
   cudaStream_t st = (cudaStream_t)stream;
   const bool ln = ln_gamma != nullptr, f32 = out_dtype == SMER_DT_F32, rs = resid != nullptr;
-#define DL_LAUNCH(LN_, RELU_, RESID_, F32_) decode_linear_kernel<LN_, RELU_, RESID_, F32_><<<grid, DL_THREADS, 0, st>>>(p)
+#define DL_LAUNCH(LN_, RELU_, RESID_, F32_) smer_launch_pdl(decode_linear_kernel<LN_, RELU_, RESID_, F32_>, grid, dim3(DL_THREADS), 0, st, p)
   if (ln) {
     if (f32) DL_LAUNCH(true, false, false, true);
     else if (relu) DL_LAUNCH(true, true, false, false);

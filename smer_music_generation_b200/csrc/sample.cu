@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(128) sample_kernel(smer_sample_args a) {
   __shared__ int chosen, shared_keep;
   int s = blockIdx.x;
   int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (a.done && a.done[s]) return;
   const int V = a.V;
   int st = a.state ? a.state[s] : 0;
@@ -297,7 +299,7 @@ extern "C" int smer_sample_masked(const smer_sample_args* a, void* stream) {
   SMER_CHECK_ARG(a->temperature > 0.0, "smer_sample_masked: temperature must be positive");
   SMER_CHECK_ARG(!a->tok_buf || (a->cur_len && a->span_start && a->span_idx && a->n_spans && a->done && a->gen_count),
                  "smer_sample_masked: stream bookkeeping needs cur_len/span_start/span_idx/n_spans/done/gen_count");
-  sample_kernel<<<a->n_seq, 128, 0, (cudaStream_t)stream>>>(*a);
+  smer_launch_pdl(sample_kernel, dim3(a->n_seq), dim3(128), 0, (cudaStream_t)stream, *a);
   SMER_CHECK_LAUNCH("smer_sample_masked");
   return SMER_OK;
 }

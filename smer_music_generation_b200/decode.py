@@ -349,7 +349,8 @@ class InfillDecoder:
     def _step_small(self):
         """The decode step for small batches (n <= 256 pieces per GPU, bf16): every projection through the small-M kernel
         (a 64-row x 8-column slab per CTA, so that even a [n, 512] x [512, 512] product covers the GPU) with the LayerNorms
-        fused into the prologue of the product that consumes them -- 36 launches per token instead of 48."""
+        fused into the prologue of the product that consumes them -- 35 launches per token instead of 48, each a programmatic
+        dependent launch (csrc/common.cuh smer_launch_pdl) so that a kernel's weight loads start while its predecessor drains."""
         m, b = self.m, self.buf
         d = m.d_model
         n, L, S = self.n, self.max_len, self.S
@@ -383,10 +384,10 @@ class InfillDecoder:
             x_in, prev_ln = b["z3"], lp.ln[2]
             launches += 8
         dn = m.transformer.decoder.norm
-        ops.layernorm_fwd(x_in, None, prev_ln[0], prev_ln[1], None, b["y3"], None, None)     # LN3 of the last layer
-        lin(b["y3"], self.fc_p[0], b["logits"], bias=self.fc_p[1], ln=(dn.weight.detach(), dn.bias.detach()))
+        # LN3 of the last layer, then the decoder's final norm, both in the prologue of the vocabulary projection
+        lin(x_in, self.fc_p[0], b["logits"], bias=self.fc_p[1], ln=prev_ln, ln2=(dn.weight.detach(), dn.bias.detach()))
         self._sample()
-        self.launches_per_step = launches + 3
+        self.launches_per_step = launches + 2
 
     def _sample(self):
         m, b = self.m, self.buf

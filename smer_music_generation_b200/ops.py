@@ -348,12 +348,13 @@ def classify_mask(mask2d, flags3):
         K.check(K.lib().smer_classify_mask(_p(mask2d), mask2d.stride(0), T, _p(flags3), K.stream()), "classify_mask")
 
 
-def decode_linear(a, w, out, bias=None, resid=None, relu=False, ln=None, ln_out=None, eps=1e-5):
-    """Small-M linear of the decode step (csrc/decode_linear.cu): out = epi(LN?(a) @ w^T + bias)."""
+def decode_linear(a, w, out, bias=None, resid=None, relu=False, ln=None, ln_out=None, ln2=None, eps=1e-5):
+    """Small-M linear of the decode step (csrc/decode_linear.cu): out = epi(LN2?(LN?(a)) @ w^T + bias)."""
     with _Timed("gemm", 2.0 * a.shape[0] * a.shape[1] * w.shape[0], 1):
         M, Kd = a.shape
         N = w.shape[0]
         K.check(K.lib().smer_decode_linear(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(resid),
                                            resid.stride(0) if resid is not None else 0, _p(out), out.stride(0), K.dt(out), M, N, Kd,
                                            int(relu), _p(ln[0]) if ln else 0, _p(ln[1]) if ln else 0, _p(ln_out),
-                                           ln_out.stride(0) if ln_out is not None else 0, eps, K.stream()), "decode_linear")
+                                           ln_out.stride(0) if ln_out is not None else 0,
+                                           _p(ln2[0]) if ln2 else 0, _p(ln2[1]) if ln2 else 0, eps, K.stream()), "decode_linear")

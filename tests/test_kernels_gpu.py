@@ -568,7 +568,8 @@ def test_sampler_empirical_histogram(dev, oracle):
 
 # ---------------------------------------------------------------------------------------- decode: small-M linear
 @pytest.mark.parametrize("M,N,K,mode", [(5, 512, 512, "plain"), (130, 1536, 512, "ln"), (64, 320, 512, "ln_f32"),
-                                        (128, 512, 2048, "resid"), (200, 2048, 512, "ln_relu"), (1, 512, 512, "ln_resid")])
+                                        (128, 512, 2048, "resid"), (200, 2048, 512, "ln_relu"), (1, 512, 512, "ln_resid"),
+                                        (77, 310, 512, "ln_ln_f32")])
 def test_decode_linear_vs_torch(dev, M, N, K, mode):
     """csrc/decode_linear.cu: out = epi(LN?(a) @ w^T + b) for the decode step's few rows, every epilogue / prologue."""
     ops, Kc = _ops()
@@ -579,17 +580,58 @@ def test_decode_linear_vs_torch(dev, M, N, K, mode):
     resid = torch.randn(M, N, generator=g).to(dev).bfloat16() if "resid" in mode else None
     gamma, beta = (torch.rand(K, generator=g) + 0.5).to(dev), (torch.randn(K, generator=g) * 0.1).to(dev)
     ln = (gamma, beta) if mode.startswith("ln") else None
-    out = torch.empty(M, N, dtype=torch.float32 if mode == "ln_f32" else torch.bfloat16, device=dev)
+    out = torch.empty(M, N, dtype=torch.float32 if mode.endswith("f32") else torch.bfloat16, device=dev)
     y = torch.empty(M, K, dtype=torch.bfloat16, device=dev) if ln else None
-    ops.decode_linear(a, w, out, bias=bias, resid=resid, relu="relu" in mode, ln=ln, ln_out=y)
+    ln2 = ((torch.rand(K, generator=g) + 0.5).to(dev), (torch.randn(K, generator=g) * 0.1).to(dev)) if "ln_ln" in mode else None
+    ops.decode_linear(a, w, out, bias=bias, resid=resid, relu="relu" in mode, ln=ln, ln_out=y, ln2=ln2)
     x = a.float()
     if ln:
         x = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5)
         assert rel(y, x) < 1e-2
         x = x.bfloat16().float()                    # the kernel feeds the tensor cores the bf16-rounded normalised rows
+    if ln2:                                         # norm3 of the last layer, then the decoder's final norm
+        x = torch.nn.functional.layer_norm(x, (K,), ln2[0], ln2[1], 1e-5).bfloat16().float()
     ref = x @ w.float().t() + bias
     if "relu" in mode:
         ref = ref.relu()
     if resid is not None:
         ref = ref + resid.float()
     assert rel(out, ref) < (2e-3 if mode == "ln_f32" else 1e-2)
+
+
+def test_decode_chain_programmatic_launch_is_ordered(dev):
+    """The decode kernels are programmatic dependent launches (csrc/common.cuh smer_launch_pdl): a kernel may start while
+    its predecessor drains but touches activations only after griddepcontrol.wait.  A long dependent chain through ONE
+    buffer pair, replayed from a CUDA graph, must give exactly what a synchronised launch-by-launch run gives."""
+    ops, Kc = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, Kd = 96, 512
+    w = [(torch.randn(Kd, Kd, generator=g) * 0.06).to(dev).bfloat16() for _ in range(3)]
+    bias = [torch.randn(Kd, generator=g).to(dev) * 0.1 for _ in range(3)]
+    gamma, beta = (torch.rand(Kd, generator=g) + 0.5).to(dev), (torch.randn(Kd, generator=g) * 0.1).to(dev)
+    x0 = torch.randn(M, Kd, generator=g).to(dev).bfloat16()
+    bufs = [torch.empty_like(x0) for _ in range(2)]
+
+    def chain(sync):
+        bufs[0].copy_(x0)
+        for i in range(24):
+            src, dst = bufs[i % 2], bufs[(i + 1) % 2]
+            ops.decode_linear(src, w[i % 3], dst, bias=bias[i % 3], resid=src if i % 2 else None, relu=(i % 2 == 0),
+                              ln=(gamma, beta))
+            if sync:
+                torch.cuda.synchronize()
+        return bufs[0]
+
+    want = chain(True).clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        chain(False)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            chain(False)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(20):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[0], want)
