@@ -18,6 +18,7 @@
 #include "ptx.cuh"
 #include "../../include/smer_b200.h"
 #include <stdlib.h>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -105,9 +106,20 @@ struct EpiParams {
 // (the per-element flag branches and dead operand loads were ~1/3 of the epilogue's instructions).
 enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RELU_DROP = 3, EPI_RESID = 4, EPI_GATE = 5, EPI_ATOMIC = 6 };
 
+// The bias / ReLU / dropout epilogues with bf16 output need no second operand, so they run in the accumulator's own
+// layout (lane = row, 64 consecutive columns per round) and leave through the TMA: pack to bf16, 8 x 16-byte shared
+// stores into a 128-byte-swizzled 32 x 64 box, one cp.async.bulk.tensor store per warp and round.  The generic path's
+// fp32 staging + read-back + per-lane global stores kept the L1 data pipe at 67 % (+26 % for the operand fill), which
+// is what held the K = 512 products at 61 % tensor-pipe activity (profiles/r02_e_gemm_qkv_ncu.txt).
+template <typename TC, int EPI>
+__host__ __device__ constexpr bool row_epilogue() {
+  return sizeof(TC) == 2 && (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RELU_DROP);
+}
+
 template <bool A_MN, bool B_MN, typename TC, int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, EpiParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, EpiParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using C = Cfg<BN, CTAS>;
@@ -133,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (row_epilogue<TC, EPI>()) ptx::prefetch_tmap(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar + s, 1);
       ptx::mbar_init(empty_bar + s, 1);
@@ -237,6 +250,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int chalf = (warp - 2) >> 2;              // which 64 of the tile's 128 columns
     const uint32_t stage_addr = ptx::smem_u32(sEpi + (warp - 2) * STAGE_EPI);
     int item = 0;
+    if constexpr (row_epilogue<TC, EPI>()) {
+      for (int w = cid; w < total; w += nworkers, ++item) {
+        const int rem = w % tiles_mn;
+        const int m0 = (rem / p.tiles_n) * (BM * CTAS) + rank * BM, n0 = (rem % p.tiles_n) * BN;
+        const int acc = item & 1;
+        const int row0 = m0 + quarter * 32;             // the 32 rows of this warp's TMEM lane quarter
+        ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
+        // rounds of 64 columns = one 128-byte row per lane = one 32 x 64 TMA box (4 KB staging, SWIZZLE_128B)
+#pragma unroll
+        for (int hp = 0; hp < BN / 128; ++hp) {
+          const int col0 = n0 + chalf * (BN / 2) + hp * 64;
+          uint32_t pk[32];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_addr + hp * 64 + sub * 32, r);
+            float4 bv[8];                               // the same 32 bias values in every lane (uniform 16-byte loads)
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              bv[u] = col0 + sub * 32 + 4 * u < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + sub * 32) + u)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            ptx::tmem_ld_wait();
+            if (hp == BN / 128 - 1 && sub == 1) {       // the whole accumulator part has left TMEM
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CTAS == 2) ptx::mbar_arrive_leader(tmem_empty_bar + acc);
+                else ptx::mbar_arrive(tmem_empty_bar + acc);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float v[4] = {__uint_as_float(r[4 * u]) + bv[u].x, __uint_as_float(r[4 * u + 1]) + bv[u].y,
+                            __uint_as_float(r[4 * u + 2]) + bv[u].z, __uint_as_float(r[4 * u + 3]) + bv[u].w};
+              if (f_relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if (f_drop) {
+                float mk[4];
+                dropout4k(dkey, (uint64_t)(((long long)(row0 + lane) * p.ldc + col0 + sub * 32 + 4 * u) >> 2), p.thr,
+                          p.inv_keep, mk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] *= mk[e];
+              }
+              pk[sub * 16 + 2 * u] = pack_bf16x2(v[0], v[1]);
+              pk[sub * 16 + 2 * u + 1] = pack_bf16x2(v[2], v[3]);
+            }
+          }
+          if (col0 >= p.N || row0 >= p.M) continue;     // box entirely outside C (warp-uniform)
+          // the previous store of this warp has finished reading the staging buffer
+          if (lane == 0) ptx::tma_wait_group_read<0>();
+          __syncwarp();
+          const uint32_t rowbase = stage_addr + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)                   // SWIZZLE_128B: chunk ^= row % 8
+            st_shared_v4(rowbase + (((uint32_t)c ^ (lane & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_c, stage_addr, col0, row0);
+            ptx::tma_commit_group();
+          }
+        }
+      }
+      if (lane == 0) ptx::tma_wait_group0();            // every store has landed before the CTA's smem goes away
+      __syncwarp();
+    } else
     for (int w = cid; w < total; w += nworkers, ++item) {
       const int sp = w / tiles_mn, rem = w - sp * tiles_mn;
       const int m0 = (rem / p.tiles_n) * (BM * CTAS) + rank * BM, n0 = (rem % p.tiles_n) * BN;
@@ -425,17 +508,17 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void* ptr;
   long long inner, outer, pitch;
-  int box_inner, box_outer;
+  int box_inner, box_outer, swizzle;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch == o.pitch && box_inner == o.box_inner &&
-           box_outer == o.box_outer;
+           box_outer == o.box_outer && swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&h](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.pitch); mix(k.box_inner); mix(k.box_outer);
+    mix(k.inner); mix(k.outer); mix(k.pitch); mix(k.box_inner); mix(k.box_outer); mix(k.swizzle);
     return h;
   }
 };
@@ -443,11 +526,11 @@ struct MapKeyHash {
 }  // namespace
 
 // bf16 2-D tensor map: `inner` contiguous elements per row, `outer` rows, row pitch in elements.
-int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
-                        int box_inner, int box_outer) {
+int smer_make_tmap_bf16_sw(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
+                           int box_inner, int box_outer, int swizzle_bytes) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, inner, outer, pitch, box_inner, box_outer};
+  MapKey key{ptr, inner, outer, pitch, box_inner, box_outer, swizzle_bytes};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -464,8 +547,8 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     smer_set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld pitch=%lld box=%dx%d", (int)r, inner, outer,
                    pitch, box_inner, box_outer);
@@ -475,6 +558,11 @@ int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long
   if (cache.size() > 4096) cache.clear();
   cache[key] = *out;
   return SMER_OK;
+}
+
+int smer_make_tmap_bf16(CUtensorMap* out, const void* ptr, long long inner, long long outer, long long pitch,
+                        int box_inner, int box_outer) {
+  return smer_make_tmap_bf16_sw(out, ptr, inner, outer, pitch, box_inner, box_outer, 128);
 }
 
 // fp32 tensor map (SWIZZLE_128B, 32 floats = 128 bytes inner box): the dQ accumulation buffer of the fused attention
@@ -504,14 +592,22 @@ int smer_make_tmap_f32(CUtensorMap* out, const void* ptr, long long inner, long 
 
 template <bool A_MN, bool B_MN, typename TC, int BN, int EPI, int CTAS = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& p, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> attr_set{0ull};         // one bit per device: the attribute is per (function, device)
   auto kern = gemm_tc_kernel<A_MN, B_MN, TC, BN, EPI, CTAS>;
-  if (!attr_set) {
+  int dev = 0;
+  SMER_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(attr_set.load(std::memory_order_acquire) & bit)) {
     SMER_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CTAS>::SMEM_BYTES));
-    attr_set = true;
+    attr_set.fetch_or(bit, std::memory_order_release);
+  }
+  CUtensorMap tc = ta;                               // (unused by the epilogues that store through the LSU)
+  if (row_epilogue<TC, EPI>()) {
+    int rc = smer_make_tmap_bf16_sw(&tc, p.C, p.N, p.M, p.ldc, 64, 32, 128);
+    if (rc) return rc;
   }
   if (CTAS == 1) {
-    kern<<<grid, GEMM_THREADS, Cfg<BN, CTAS>::SMEM_BYTES, st>>>(ta, tb, p);
+    kern<<<grid, GEMM_THREADS, Cfg<BN, CTAS>::SMEM_BYTES, st>>>(ta, tb, tc, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;                       // 2 x number of CTA pairs
@@ -525,7 +621,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiPa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SMER_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+    SMER_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, p));
   }
   return SMER_OK;
 }
