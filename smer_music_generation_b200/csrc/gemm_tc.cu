@@ -81,6 +81,11 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void ld_shared_v4(uint32_t addr, float* v) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
 }
@@ -106,14 +111,15 @@ struct EpiParams {
 // (the per-element flag branches and dead operand loads were ~1/3 of the epilogue's instructions).
 enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_BIAS_RELU_DROP = 3, EPI_RESID = 4, EPI_GATE = 5, EPI_ATOMIC = 6 };
 
-// The bias / ReLU / dropout epilogues with bf16 output need no second operand, so they run in the accumulator's own
+// The bias / ReLU / dropout epilogues with bf16 output need no second operand (and the gate epilogue of the FFN
+// backward reads its activation row-wise, 128 contiguous bytes per lane and round), so they run in the accumulator's own
 // layout (lane = row, 64 consecutive columns per round) and leave through the TMA: pack to bf16, 8 x 16-byte shared
 // stores into a 128-byte-swizzled 32 x 64 box, one cp.async.bulk.tensor store per warp and round.  The generic path's
 // fp32 staging + read-back + per-lane global stores kept the L1 data pipe at 67 % (+26 % for the operand fill), which
 // is what held the K = 512 products at 61 % tensor-pipe activity (profiles/r02_e_gemm_qkv_ncu.txt).
 template <typename TC, int EPI>
 __host__ __device__ constexpr bool row_epilogue() {
-  return sizeof(TC) == 2 && (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RELU_DROP);
+  return sizeof(TC) == 2 && (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_RELU_DROP || EPI == EPI_GATE);
 }
 
 template <bool A_MN, bool B_MN, typename TC, int BN, int EPI, int CTAS>
@@ -256,6 +262,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int m0 = (rem / p.tiles_n) * (BM * CTAS) + rank * BM, n0 = (rem % p.tiles_n) * BN;
         const int acc = item & 1;
         const int row0 = m0 + quarter * 32;             // the 32 rows of this warp's TMEM lane quarter
+        // gate operand (the stored activation h = dropout(relu(.)): h > 0 <=> kept and active): this lane's row, both
+        // rounds, issued before the accumulator wait
+        uint4 graw[EPI == EPI_GATE ? BN / 128 : 1][EPI == EPI_GATE ? 8 : 1];
+        if constexpr (EPI == EPI_GATE) {
+          const bool rv = row0 + lane < p.M;
+          const bf16* grow = reinterpret_cast<const bf16*>(p.resid) + (long long)(row0 + lane) * p.ldr;
+#pragma unroll
+          for (int hp = 0; hp < BN / 128; ++hp)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int col = n0 + chalf * (BN / 2) + hp * 64 + c * 8;
+              graw[hp][c] = rv && col < p.N ? __ldg(reinterpret_cast<const uint4*>(grow + col)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
         ptx::mbar_wait(tmem_full_bar + acc, (item >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16) + chalf * (BN / 2);
@@ -271,8 +291,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float4 bv[8];                               // the same 32 bias values in every lane (uniform 16-byte loads)
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-              bv[u] = col0 + sub * 32 + 4 * u < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + sub * 32) + u)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+              bv[u] = f_bias && col0 + sub * 32 + 4 * u < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + sub * 32) + u)
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             ptx::tmem_ld_wait();
             if (hp == BN / 128 - 1 && sub == 1) {       // the whole accumulator part has left TMEM
               ptx::tc_fence_before();
@@ -289,6 +309,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (f_relu) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if constexpr (EPI == EPI_GATE) {
+                const uint4 gq = graw[hp][sub * 4 + (u >> 1)];
+                const uint32_t g0 = (u & 1) ? gq.z : gq.x, g1 = (u & 1) ? gq.w : gq.y;     // 4 bf16 of h
+                v[0] = __uint_as_float(g0 << 16) > 0.f ? v[0] * p.inv_keep : 0.f;
+                v[1] = __uint_as_float(g0 & 0xFFFF0000u) > 0.f ? v[1] * p.inv_keep : 0.f;
+                v[2] = __uint_as_float(g1 << 16) > 0.f ? v[2] * p.inv_keep : 0.f;
+                v[3] = __uint_as_float(g1 & 0xFFFF0000u) > 0.f ? v[3] * p.inv_keep : 0.f;
               }
               if (f_drop) {
                 float mk[4];
@@ -314,6 +342,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (lane == 0) {
             ptx::tma_store_2d(&tmap_c, stage_addr, col0, row0);
             ptx::tma_commit_group();
+          }
+          if constexpr (EPI == EPI_GATE) {
+            // column sums of the stored tile (the bias gradient of linear1): lane l adds up columns 2l, 2l+1 over the
+            // 32 staged rows (one conflict-free 128-byte row per load; rows >= M and columns >= N hold zeros)
+            if (p.colsum != nullptr) {
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const uint32_t wv = ld_shared_u32(stage_addr + rr * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)rr & 7u)) << 4) + (lane & 3) * 4);
+                s0 += __uint_as_float(wv << 16);
+                s1 += __uint_as_float(wv & 0xFFFF0000u);
+              }
+              if (col0 + 2 * lane < p.N)
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p.colsum + col0 + 2 * lane), "f"(s0), "f"(s1) : "memory");
+            }
           }
         }
       }
