@@ -132,7 +132,12 @@ class Ctx:
                 import torch.distributed as dist
                 # (NCCL's CTA count is left at its default: capping it to 2 / 4 / 8 CTAs made the bucket all-reduces too slow to
                 #  hide behind the backward kernels -- exposed time 0.76 / 0.72 / 0.47 ms against 0.30 ms at 16, 2 GPUs)
-                dist.init_process_group("nccl", device_id=self.dev)
+                # The collectives run on a high-priority stream: the persistent GEMM / attention grids hold every SM, so a
+                # default-priority all-reduce kernel only gets its CTAs placed when a compute kernel happens to leave room.
+                opts = None
+                if os.environ.get("SMER_NCCL_HIGH_PRIORITY", "1") != "0":
+                    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                dist.init_process_group("nccl", device_id=self.dev, pg_options=opts)
                 self.pg = dist.group.WORLD
 
     def barrier(self):

@@ -48,6 +48,10 @@ extern "C" {
 #define SMER_XENT_MAX_SUMS 16
 
 int smer_version(void);
+/* Data-parallel runs: SMs (even count) the persistent GEMM / attention-forward grids leave to the collective kernels that
+ * overlap them (reference: DistributedDataParallel's bucketed all-reduce, train.py:629-642).  0 by default; also read
+ * from SMER_RESERVED_SMS at load time. */
+int smer_set_reserved_sms(int n);
 const char* smer_last_error(void);
 /* 1 when the running device is compute capability 10.x (sm_100a cubins loadable) */
 int smer_device_ok(void);

@@ -153,7 +153,7 @@ class TrainEngine:
         if process_group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(process_group)
-        self.comm_stream = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
+        self.comm_stream = torch.cuda.Stream(device=self.dev, priority=-1) if self.world > 1 else None
         self.buckets = GradBuckets(model, self.grads, n_buckets, process_group, self.comm_stream) if self.world > 1 else None
 
     # ---- one step ---------------------------------------------------------------------
