@@ -338,7 +338,7 @@ def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e
     dev, rank = ctx.dev, ctx.rank
     world = ctx.world if pg is not None else 1
     model = build_model(cfg, dtype, dev, world=world).train()
-    eng = TrainEngine(model, lr=1e-4, eos_weight=0.8, process_group=pg)
+    eng = TrainEngine(model, lr=1e-4, eos_weight=0.8, process_group=pg, n_buckets=int(os.environ.get("SMER_DP_BUCKETS", "0")))
     nb = 4
     host = [O.synth_batch(B, S, T, seed=1234 + 17 * rank + i) for i in range(nb)]
     host = [tuple(t.pin_memory() for t in b) for b in host]
@@ -400,6 +400,26 @@ def timed_train(ctx, cfg, dtype, B, S, T, steps, warmup, pg, use_graph=True, e2e
     total = ctx.sum(toks) if pg is not None else float(toks)
     out.update(ms=ms, ms_per_step=ms / steps, value=total / (ms * 1e-3), loss=eng.loss_value(), use_graph=use_graph,
                exec_frac=attn_executed_fraction(host[0][3], host[0][4], S, T))
+    tl = os.environ.get("SMER_TIMELINE")
+    if tl:
+        # kernel timeline of three more steps (CUPTI through torch.profiler; nsys is not in the image): every rank runs the
+        # steps, rank 0 writes {name, stream, start us, duration us} per kernel -- untimed, after `value`
+        from torch.profiler import profile as _tprofile, ProfilerActivity
+        ctx.barrier()
+        if rank == 0:
+            with _tprofile(activities=[ProfilerActivity.CUDA]) as tp:
+                for i in range(3):
+                    step(devb[i % nb])
+                torch.cuda.synchronize()
+            evs = [dict(name=e.name, stream=getattr(e, "device_resource_id", None), ts=e.time_range.start, dur=e.time_range.elapsed_us())
+                   for e in tp.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+            with open(tl, "w") as f:
+                json.dump(evs, f)
+        else:
+            for i in range(3):
+                step(devb[i % nb])
+            torch.cuda.synchronize()
+        ctx.barrier()
     if e2e:
         # end to end: pinned host buffers -> H2D -> step -> loss D2H, every step
         ctx.barrier()

@@ -87,10 +87,8 @@ class GradBuckets:
         if n_buckets and n_buckets > 0:
             per = max(1, math.ceil(len(groups) / n_buckets))
             chunks = [groups[i:i + per] for i in range(0, len(groups), per)]
-        else:
-            # default: one bucket per layer (a few MB each, launched the moment that layer's backward is done); the two
-            # stack norms ride with the group signalled next; the embedding table (V x d, the only gradient that is
-            # final at the very end of backward) is ALONE in the last bucket, so the exposed tail is its 0.6 MB
+        elif n_buckets == -1:
+            # one bucket per layer, the embedding table alone in the last one (the smallest tail, the most collectives)
             chunks, pending = [], []
             for g in groups[:-1]:
                 pending.append(g)
@@ -100,6 +98,19 @@ class GradBuckets:
             if pending:
                 chunks.append(pending)
             chunks.append([groups[-1]])
+        else:
+            # default: THREE buckets -- (1) fc + the decoder stack, all-reduced while the encoder's backward runs; (2) the
+            # encoder layers but the first, behind the first layer's backward; (3) the first encoder layer + the embedding
+            # table, the exposed tail.  Measured on 8 x B200 (profiles/r02_f_dp8_timeline.txt): a 12.6-16.8 MB all-reduce
+            # costs 90-100 us alone against 364 us for all 119 MB at once, and every collective kernel holds its SMs while
+            # it waits for the slowest rank -- ten per-layer buckets kept NCCL kernels resident for 1.8 ms of a 12.9 ms
+            # step (the exposed time beyond the 0.12 ms tail was compute slowed down under them), three need ~0.5 ms.
+            first_enc = f"transformer.encoder.layers.0."
+            i_enc = groups.index("transformer.encoder.norm.")
+            dec, enc, tail = groups[:i_enc], [g for g in groups[i_enc:-1] if g != first_enc], [first_enc, groups[-1]]
+            if ne < 2:
+                dec, enc = dec + enc, []
+            chunks = [c for c in (dec, enc, tail) if c]
         self.buckets = [(c, min(spans[g][0] for g in c), max(spans[g][1] for g in c)) for c in chunks]
         self.reset()
 

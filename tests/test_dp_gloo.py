@@ -31,13 +31,19 @@ def _worker(rank, world, port, q):
         torch.manual_seed(0)
         m = ScoreTransformer(309, 32, 2, 2, 2, 64, 64, 0.0, 0.0)
         arena = GradArena(m)
-        # default layout: one bucket per layer, the embedding table alone in the last one (the exposed tail)
+        # default layout: decoder stack | encoder layers but the first | first encoder layer + embedding (the exposed tail)
         gd = GradBuckets(m, arena, 0, dist.group.WORLD, comm_stream=None)
-        assert gd.buckets[-1][0] == ["embedding."] and len(gd.buckets) == 2 + 2 + 1
-        assert gd.buckets[0][0] == ["fc.", "transformer.decoder.norm.", "transformer.decoder.layers.1."]
-        b_emb, e_emb = gd.buckets[-1][1:]
+        assert [c for c, _, _ in gd.buckets] == [
+            ["fc.", "transformer.decoder.norm.", "transformer.decoder.layers.1.", "transformer.decoder.layers.0."],
+            ["transformer.encoder.norm.", "transformer.encoder.layers.1."],
+            ["transformer.encoder.layers.0.", "embedding."]]
+        # per-layer layout: the embedding table alone in the last bucket
+        gl = GradBuckets(m, arena, -1, dist.group.WORLD, comm_stream=None)
+        assert gl.buckets[-1][0] == ["embedding."] and len(gl.buckets) == 2 + 2 + 1
+        assert gl.buckets[0][0] == ["fc.", "transformer.decoder.norm.", "transformer.decoder.layers.1."]
+        b_emb, e_emb = gl.buckets[-1][1:]
         assert e_emb - b_emb == (309 * 32 + 63) // 64 * 64
-        for gb in (gd, GradBuckets(m, arena, 4, dist.group.WORLD, comm_stream=None)):
+        for gb in (gd, gl, GradBuckets(m, arena, 4, dist.group.WORLD, comm_stream=None)):
             # every arena element belongs to exactly one bucket
             cover = torch.zeros(arena.total, dtype=torch.int32)
             for _, b, e in gb.buckets:
