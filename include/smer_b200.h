@@ -52,6 +52,11 @@ int smer_version(void);
  * overlap them (reference: DistributedDataParallel's bucketed all-reduce, train.py:629-642).  0 by default; also read
  * from SMER_RESERVED_SMS at load time. */
 int smer_set_reserved_sms(int n);
+/* Programmatic dependent launch for the decode-step kernels (smer_decode_embed / _attn / _linear, smer_sample_masked): while
+ * on, each of them may be scheduled before its predecessor in the stream has drained (it waits with griddepcontrol.wait
+ * before touching activations).  Only valid when EVERY kernel between two of them is one of them: the small-batch decode
+ * step (generation.py:528-687 at <= 256 pieces) turns it on around its launches; off by default. */
+int smer_set_pdl(int on);
 const char* smer_last_error(void);
 /* 1 when the running device is compute capability 10.x (sm_100a cubins loadable) */
 int smer_device_ok(void);

@@ -83,6 +83,7 @@ _SIGS = {
     "smer_decode_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "smer_embed_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "smer_set_reserved_sms": (_i, [_i]),
+    "smer_set_pdl": (_i, [_i]),
     "smer_decode_linear": (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _f, _vp]),
     "smer_sample_masked": (_i, [C.POINTER(SampleArgs), _vp]),
     "smer_cast2d": (_i, [_vp, _i, _ll, _vp, _i, _ll, _ll, _i, _i, _vp]),

@@ -34,6 +34,10 @@ int smer_num_sms() {
   return cached - g_reserved_sms > 2 ? cached - g_reserved_sms : 2;
 }
 
+static int g_pdl = 0;
+int smer_pdl_flag() { return g_pdl; }
+extern "C" int smer_set_pdl(int on) { g_pdl = on ? 1 : 0; return SMER_OK; }
+
 static const unsigned long long* g_seed_dev = nullptr;
 const unsigned long long* smer_seed_dev() { return g_seed_dev; }
 extern "C" int smer_set_seed_device_ptr(const uint64_t* p) {

@@ -31,13 +31,18 @@ void smer_set_error(const char* fmt, ...);
 // pdl_trigger(), and must execute pdl_wait() before it reads or writes anything a predecessor touches -- until then it may
 // only set itself up and prefetch data no kernel of the chain writes (weights).  pdl_wait() returns once the predecessor
 // grid has completed and its writes are visible, so the chain stays strictly ordered; only launch latency and prologues
-// overlap.  SMER_PDL=0 in the environment turns the attribute off (plain stream order).
+// overlap.  The attribute is only set while smer_set_pdl(1) is in effect: the small-batch decode step (every launch of
+// the chain is one of these kernels) enables it around its launches.  Mixed into the large-batch step -- the same
+// kernels between tcgen05 GEMM / LayerNorm launches that know nothing of it -- the 1024-piece run faulted (illegal
+// address; with the attribute off on any one of embed / attention / sampler it did not), so that path stays in plain
+// stream order.  SMER_PDL=0 in the environment turns the attribute off everywhere.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+int smer_pdl_flag();                 // capi.cu: set by smer_set_pdl (the small-batch decode step turns it on around its launches)
 inline bool smer_pdl_enabled() {
   static const bool on = [] { const char* e = getenv("SMER_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+  return on && smer_pdl_flag() != 0;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t smer_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -731,6 +731,9 @@ extern "C" int smer_gemm_bf16_tc(const void* A, long long lda, int a_kmajor, con
   else if (flags == 0 && resid && !bias && !p.thr) epi = EPI_RESID;
   else if (flags == SMER_EPI_RELU && bias && !resid) epi = p.thr ? EPI_BIAS_RELU_DROP : EPI_BIAS_RELU;
   else if (flags == 0 && bias && !resid && !p.thr) epi = EPI_BIAS;
+  // SMER_GEMM_ROW_EPI=0: every product through the generic (LSU-store) epilogue -- an A/B and fault-isolation switch
+  static const bool row_epi_on = [] { const char* e = getenv("SMER_GEMM_ROW_EPI"); return !(e && e[0] == '0'); }();
+  if (!row_epi_on && (epi == EPI_BIAS || epi == EPI_BIAS_RELU || epi == EPI_BIAS_RELU_DROP || epi == EPI_GATE)) epi = EPI_GENERIC;
 #define GO3(AM, BMN, T, E)                                                                          \
   (pair ? launch_gemm<AM, BMN, T, 256, E, 2>(ta, tb, p, grid, st)                                   \
         : wide ? launch_gemm<AM, BMN, T, 256, E>(ta, tb, p, grid, st) : launch_gemm<AM, BMN, T, 128, E>(ta, tb, p, grid, st))

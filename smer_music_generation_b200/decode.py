@@ -351,6 +351,14 @@ class InfillDecoder:
         (a 64-row x 8-column slab per CTA, so that even a [n, 512] x [512, 512] product covers the GPU) with the LayerNorms
         fused into the prologue of the product that consumes them -- 35 launches per token instead of 48, each a programmatic
         dependent launch (csrc/common.cuh smer_launch_pdl) so that a kernel's weight loads start while its predecessor drains."""
+        lib = K.lib()
+        lib.smer_set_pdl(1)                # every launch below is a decode-chain kernel: programmatic dependent launches
+        try:
+            self._step_small_launches()
+        finally:
+            lib.smer_set_pdl(0)
+
+    def _step_small_launches(self):
         m, b = self.m, self.buf
         d = m.d_model
         n, L, S = self.n, self.max_len, self.S

@@ -625,11 +625,15 @@ def test_decode_chain_programmatic_launch_is_ordered(dev):
     want = chain(True).clone()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        chain(False)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
+    Kc.lib().smer_set_pdl(1)                        # as the small-batch decode step does around its launches
+    try:
+        with torch.cuda.stream(side):
             chain(False)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                chain(False)
+    finally:
+        Kc.lib().smer_set_pdl(0)
     torch.cuda.current_stream().wait_stream(side)
     for _ in range(20):
         graph.replay()
