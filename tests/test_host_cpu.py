@@ -29,6 +29,16 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.smer_device_ok() == 0            # no GPU in the build container
 
 
+def test_library_knobs_validate_their_arguments(lib):
+    """The process-wide knobs of the C ABI need no device: the SM reservation for data-parallel runs takes an even count in
+    [0, 64] and reports anything else through smer_last_error; the decode step's launch-mode toggle accepts 0 / 1."""
+    assert lib.smer_set_reserved_sms(3) != 0
+    assert b"even count" in lib.smer_last_error()
+    assert lib.smer_set_reserved_sms(66) != 0 and lib.smer_set_reserved_sms(-2) != 0
+    assert lib.smer_set_reserved_sms(8) == 0 and lib.smer_set_reserved_sms(0) == 0
+    assert lib.smer_set_pdl(1) == 0 and lib.smer_set_pdl(0) == 0
+
+
 def test_ctypes_structs_match_header_sizes(lib):
     """sizeof of the argument structs as nvcc laid them out == ctypes' layout."""
     import ctypes as C

@@ -599,6 +599,26 @@ def test_decode_linear_vs_torch(dev, M, N, K, mode):
     assert rel(out, ref) < (2e-3 if mode == "ln_f32" else 1e-2)
 
 
+def test_gemm_with_reserved_sms_is_unchanged(dev):
+    """smer_set_reserved_sms only shortens the persistent grids (data-parallel runs leave SMs to the collectives): the work
+    list is re-dealt over fewer CTAs / CTA pairs, the product is bit-identical."""
+    ops, Kc = _ops()
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(4096 + 40, 512, generator=g).to(dev).bfloat16()
+    w = (torch.randn(1536, 512, generator=g) * 0.05).to(dev).bfloat16()
+    bias = torch.randn(1536, generator=g).to(dev)
+    out0, out1 = torch.empty(a.shape[0], 1536, dtype=torch.bfloat16, device=dev), torch.empty(a.shape[0], 1536, dtype=torch.bfloat16, device=dev)
+    ops.gemm_nt(a, w, out0, bias=bias)
+    assert Kc.lib().smer_set_reserved_sms(16) == 0
+    try:
+        ops.gemm_nt(a, w, out1, bias=bias)
+    finally:
+        Kc.lib().smer_set_reserved_sms(0)
+    torch.cuda.synchronize()
+    assert torch.equal(out0, out1)
+    assert rel(out0, a.float() @ w.float().t() + bias) < 1e-2
+
+
 def test_decode_chain_programmatic_launch_is_ordered(dev):
     """The decode kernels are programmatic dependent launches (csrc/common.cuh smer_launch_pdl): a kernel may start while
     its predecessor drains but touches activations only after griddepcontrol.wait.  A long dependent chain through ONE
