@@ -8,10 +8,12 @@
 // Persistent: one CTA per SM walks a static list of (128x128 tile, K-split) work items, N fastest
 // so that concurrently running CTAs share A rows in L2.  K step 64, 6-stage smem ring (192 KB)
 // that keeps filling across work items; TWO 128-column fp32 accumulators in TMEM so the epilogue
-// of item i overlaps the MMAs of item i+1.  Epilogue (8 warps): TMEM -> registers -> per-warp smem
-// transpose (so that one store instruction covers 4 full 128-byte row segments instead of 32
-// scattered rows) -> bias/ReLU/dropout/residual/gate -> 16-byte global stores / fp32 split-K
-// reductions; residual and gate operands are read with the same coalesced mapping.
+// of item i overlaps the MMAs of item i+1.  Epilogue (8 warps), two paths (row_epilogue<> below):
+//   bias / ReLU / dropout / gate with bf16 output: math in the accumulator's layout (lane = row), bf16
+//   pack, swizzled 32 x 64 staging box, one cp.async.bulk.tensor store per warp and round;
+//   residual / fp32 split-K / generic: TMEM -> registers -> per-warp fp32 smem transpose (so that one
+//   store instruction covers 4 full 128-byte row segments instead of 32 scattered rows) -> 16-byte
+//   global stores / fp32 reductions; the residual operand is read with the same coalesced mapping.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue (TMEM lane quarter
 // = warp_idx % 4, column half = (warp_idx - 2) / 4).
 #include "common.cuh"
