@@ -119,6 +119,29 @@ def test_grad_arena_layout():
     assert 0 < b < e <= a.total
 
 
+def test_gradient_bucket_layouts_cover_the_arena():
+    """trainer.GradBuckets: the default three buckets (decoder stack | encoder layers but the first | first encoder layer +
+    embedding), its degenerate form for a one-layer encoder, and the per-layer layout are contiguous, disjoint and complete."""
+    from smer_music_generation_b200 import ScoreTransformer
+    from smer_music_generation_b200.trainer import GradArena, GradBuckets
+    for ne, nd in ((1, 2), (3, 1), (2, 2)):
+        m = ScoreTransformer(309, 32, 2, ne, nd, 64, 64, 0.0, 0.0)
+        arena = GradArena(m)
+        for nb in (0, -1, 2):
+            gb = GradBuckets(m, arena, nb, None, comm_stream=None)
+            cover = torch.zeros(arena.total, dtype=torch.int32)
+            for _, b, e in gb.buckets:
+                assert b < e
+                cover[b:e] += 1
+            assert int(cover.min()) == 1 and int(cover.max()) == 1, (ne, nd, nb)
+            flat = [g for c, _, _ in gb.buckets for g in c]
+            assert flat == gb.groups                      # buckets follow the order in which backward signals the groups
+        gd = GradBuckets(m, arena, 0, None, comm_stream=None)
+        assert gd.buckets[-1][0] == ["transformer.encoder.layers.0.", "embedding."]
+        assert len(gd.buckets) == (2 if ne < 2 else 3)
+        assert gd.buckets[0][0][0] == "fc." and all("encoder.layers" not in g for g in gd.buckets[0][0])
+
+
 def test_install_as_reference_modules():
     import sys
     import smer_music_generation_b200 as pkg
